@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — feature-extractor front-end throughput (points/sec on 1024-point clouds) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cu_dg|sph_dg] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+A "step" is one pass of the front end (k-NN -> fused gather+PPF; coordinate prologue ->
+voxelize -> trilinear devoxelize -> DGCNN voxel-neighbour edge features) over one batch of 32 synthetic
+ModelNet40-shaped clouds of 1024 points PER GPU (weak scaling: clouds are sharded by rank, no data-path collective).
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      dominant op (voxelize = vox_prepare + vox_fill: the dense [C, r^3] grid write), algorithmic bytes per
+                launch / CUDA-event duration of that op measured live, against MEASURED_PEAKS.json's HBM GB/s
+  cpu_baseline  the C oracle port (oracle/ri_oracle.c, OpenMP over clouds) timed on this box's host cores on a
+                bounded sample of the same workload (rank 0, N=1 only)
+  e2e           the same metric through the host-facing call FrontEnd.run_staged(): pinned host inputs -> H2D ->
+                step -> D2H of the per-point outputs, every step
+`--impl reference` times the UNMODIFIED reference kernels (oracle/_ref, the reference's own CUDA backend recompiled
+for sm_100a — the reference has no CPU implementation: every op CHECK_CUDAs) through the reference's op sequence on
+the same workload with the same host<->device copies; if that library is absent it times the oracle port on the host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "feature-extractor points/sec (1024-pt clouds)"
+UNIT = "points/s"
+WORKLOADS = {
+    # BASELINE.json configs[1]: cu_dg variant (cube voxelization + DGCNN), 32 x 1024 on 1 B200; C = 3 + 4 + 64
+    # input channels of the registration model's first PVConv
+    "cu_dg": dict(voxel_shape="cube", B=32, N=1024, C=71, k=20, r=32,
+                  name="cu_dg front end: 32 x 1024 pts with normals, k=20 KNN+PPF, cube voxelize r=32 C=71, "
+                       "trilinear devox, DGCNN edge gather (BASELINE configs[1])"),
+    # BASELINE.json configs[0]: sph_dg classification front end; C = 3 + 64
+    "sph_dg": dict(voxel_shape="spherical", B=32, N=1024, C=67, k=20, r=32,
+                   name="sph_dg front end: 32 x 1024 pts with normals, k=20 KNN+PPF, spherical voxelize r=32 C=67, "
+                        "spherical trilinear devox, DGCNN edge gather (BASELINE configs[0])"),
+}
+RING = 3          # independent input/output buffer sets cycled between timed steps (footprint > L2)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the benchmark runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 6:
+                try:
+                    self.samples.append((time.time(), float(f[0]), float(f[1]), f[2:6]))
+                except ValueError:
+                    pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self, windows):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+        inside = [s for s in self.samples if any(a <= s[0] <= b for a, b in windows)]
+        note = "sampled inside the timed regions"
+        if not inside:
+            inside, note = self.samples, "timed regions shorter than the 100 ms sampling period: whole-run samples"
+        mhz = sorted(s[1] for s in inside)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in inside for n, v in zip(names, s[3]) if v.lower().startswith("active")})
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": inside[0][2], "reasons": reasons,
+                "samples": len(inside), "note": note}
+
+
+def traffic_from_profile(workload):
+    """dram bytes per launch of the dominant op from the committed ncu capture, if one exists (else null)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(workload)
+    except Exception:
+        return None
+
+
+# ===================================================================================================== ours
+def run_ours(args, rank, world, local):
+    import torch
+    import ri_b200
+    from ri_b200 import shard, synth
+
+    wl = WORKLOADS[args.workload]
+    B, N, C, k, r = wl["B"], wl["N"], wl["C"], wl["k"], wl["r"]
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    sampler = ClockSampler(local) if rank == 0 else None
+
+    # per-rank shard of the (world * B)-cloud job, RING independent batches
+    engines, batches = [], []
+    for q in range(RING):
+        pts = synth.make_clouds(B, N, seed=1000 + 17 * rank + q)
+        feats = synth.make_features(B, C, N, seed=1000 + 17 * rank + q)
+        fe = ri_b200.FrontEnd(B, N, C, k=k, r=r, voxel_shape=wl["voxel_shape"], normalize=False, device=dev)
+        fe.h_points.copy_(torch.from_numpy(pts)); fe.h_features.copy_(torch.from_numpy(feats))
+        fe.load(fe.h_points, fe.h_features)
+        engines.append(fe); batches.append((pts, feats))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+
+    def timed(fn, steps):
+        barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize(); barrier()
+        return shard.max_over_ranks(e0.elapsed_time(e1), dev), (t0, time.time())
+
+    windows = []
+    # ---- device-resident throughput (`value`)
+    for i in range(max(args.warmup, RING)):
+        engines[i % RING].forward()
+    ms, w = timed(lambda i: engines[i % RING].forward(), args.steps); windows.append(w)
+    pts_per_step = world * B * N
+    value = pts_per_step * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host-facing call (`e2e`)
+    for i in range(max(3, min(args.warmup, 5))):
+        engines[i % RING].run_staged()
+    e2e_steps = max(1, min(args.steps, 200))
+    ms_e2e, w = timed(lambda i: engines[i % RING].run_staged(), e2e_steps); windows.append(w)
+    e2e_value = pts_per_step * e2e_steps / (ms_e2e * 1e-3)
+
+    # ---- dominant op in isolation: voxelize (prepare + fill), CUDA events on the launching stream
+    L = ri_b200._lib.lib
+    fn = L.ri_cube_voxelize_f32 if wl["voxel_shape"] == "cube" else L.ri_sph_voxelize_f32
+    coord_of = lambda fe: (fe._vox_coords if wl["voxel_shape"] == "cube" else fe.norm_coords)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def vox_only(i):
+        fe = engines[i % RING]
+        rc = fn(fe.features.data_ptr(), coord_of(fe).data_ptr(), B, C, N, r, fe.grid.data_ptr(), fe.ind.data_ptr(),
+                fe.cnt.data_ptr(), fe._ws.data_ptr(), fe._ws_bytes, st)
+        assert rc == 0
+    for i in range(RING):
+        vox_only(i)
+    vox_steps = max(3, min(args.steps, 300))
+    ms_vox, w = timed(vox_only, vox_steps); windows.append(w)
+    alg = engines[0].algorithmic_bytes()
+    peak, peak_src = measured_peaks()
+    vox_gbs = alg["voxelize"] / (ms_vox / vox_steps * 1e-3) / 1e9
+    step_gbs = alg["total"] / (ms / args.steps * 1e-3) / 1e9
+
+    if rank != 0:
+        return
+    sampler.stop()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "clouds_per_gpu": B, "points_per_cloud": N, "k": k, "resolution": r,
+                   "channels": C, "voxel_shape": wl["voxel_shape"], "parallelism": "clouds sharded by rank (dp%d)" % world,
+                   "l2": "inputs larger than L2: %d independent batches cycled, %.0f MB written per step" %
+                         (RING, (alg["voxelize"] + alg["devox"] + alg["edge"] + alg["knn_ppf"]) / 1e6),
+                   "cuda_graph": True, "overlap": "k-NN/PPF branch on a side stream under the voxel branch"},
+        "roofline": {"bound": "hbm", "kernel": "voxelize (vox_prepare + vox_fill)", "achieved": vox_gbs, "peak": peak,
+                     "unit": "GB/s", "frac": vox_gbs / peak, "traffic": traffic_from_profile(args.workload),
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg["voxelize"],
+                     "ms_per_launch": ms_vox / vox_steps,
+                     "whole_step": {"algorithmic_bytes": alg["total"], "achieved": step_gbs, "frac": step_gbs / peak}},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": engines[0].h2d_bytes,
+                "d2h_bytes_per_step": engines[0].d2h_bytes, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+        "gpu_launches": ri_b200.FrontEnd.KERNELS_PER_STEP * args.steps,
+        "clocks": sampler.summary(windows),
+    }
+    if world == 1:
+        line["cpu_baseline"] = cpu_port_baseline(wl, batches[0])
+    print(json.dumps(line))
+
+
+def cpu_port_step(wl, pts, feats, o):
+    """The same front-end step with the C oracle port (OpenMP over clouds)."""
+    import numpy as np
+    B, N, C, k, r = pts.shape[0], wl["N"], wl["C"], wl["k"], wl["r"]
+    xyz, nrm = np.ascontiguousarray(pts[:, :3]), np.ascontiguousarray(pts[:, 3:])
+    _, idx = o.knn_one(xyz, xyz, k)
+    gi = np.broadcast_to(idx.reshape(B, 1, k * N), (B, 3, k * N))
+    o.ppf(np.broadcast_to(xyz[:, :, None, :], (B, 3, k, N)).reshape(B, 3, k * N), np.take_along_axis(xyz, gi, 2),
+          np.broadcast_to(nrm[:, :, None, :], (B, 3, k, N)).reshape(B, 3, k * N), np.take_along_axis(nrm, gi, 2))
+    if wl["voxel_shape"] == "spherical":
+        avg, ind, nc = o.spherical_voxelization_module(feats, xyz, r)
+        o.spherical_trilinear_devoxelize(nc, avg, ind, r)
+    else:
+        avg, ind, nc = o.voxelization_module(feats, xyz, r, normalize=False)
+        o.trilinear_devoxelize(nc, avg, r)
+    o.voxel_edge_gather(avg, feats, ind)
+
+
+def cpu_port_baseline(wl, batch, reps=3):
+    from oracle import cpu_oracle as o
+    o.build()
+    pts, feats = batch
+    nb = min(pts.shape[0], 32)
+    cpu_port_step(wl, pts[:2], feats[:2], o)              # warm-up (library load, page faults)
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_port_step(wl, pts[:nb], feats[:nb], o)
+        best = min(best, time.perf_counter() - t0)
+    return {"value": nb * wl["N"] / best, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": "%d clouds x %d pts, best of %d passes of the C oracle port (OpenMP over clouds, %d threads)" %
+                      (nb, wl["N"], reps, os.cpu_count())}
+
+
+# ================================================================================================ reference
+def run_reference(args, rank, world, local):
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    B, N, C, k, r = wl["B"], wl["N"], wl["C"], wl["k"], wl["r"]
+    base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": wl["name"], "clouds_per_gpu": B, "points_per_cloud": N, "k": k,
+                                            "resolution": r, "channels": C, "voxel_shape": wl["voxel_shape"]}}
+    sys.path.insert(0, os.path.join(ROOT, "point-cloud-registration-based-on-rotation-invariant-feature_b200"))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ri_synth", os.path.join(
+        ROOT, "point-cloud-registration-based-on-rotation-invariant-feature_b200", "synth.py"))
+    synth = importlib.util.module_from_spec(spec); spec.loader.exec_module(synth)
+    pts = synth.make_clouds(B, N, seed=1000); feats = synth.make_features(B, C, N, seed=1000)
+
+    ref = None
+    try:
+        import torch
+        from oracle.build_ref import load_ref
+        if torch.cuda.is_available():
+            ref = load_ref()
+    except Exception:
+        ref = None
+
+    if ref is None:                                       # no reference library on this box: the oracle port
+        cb = cpu_port_baseline(wl, (pts, feats), reps=max(1, min(args.steps, 3)))
+        base.update({"value": cb["value"], "ms_per_step": B * N / cb["value"] * 1e3, "cpu_baseline": cb,
+                     "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(base))
+        return
+
+    import torch
+    torch.cuda.set_device(0)
+    dev = "cuda:0"
+    hp = torch.from_numpy(pts).pin_memory(); hf = torch.from_numpy(feats).pin_memory()
+    out_h = {}
+
+    def step(host):
+        """Reference op sequence for the same front end, through the reference backend's own functions
+        (bindings.cpp:13-56) and the torch glue the reference uses around them."""
+        p = hp.to(dev, non_blocking=True) if host else d_p
+        f = hf.to(dev, non_blocking=True) if host else d_f
+        xyz = p[:, :3].contiguous(); nrm = p[:, 3:].contiguous()
+        _, _, idx, _ = ref.knn_forward_cuda(xyz, xyz, k)                                   # bilateral API
+        gi = idx.reshape(B, 1, k * N).expand(-1, 3, -1).long()
+        c_xyz = xyz[:, :, None, :].expand(-1, -1, k, -1).reshape(B, 3, k * N).contiguous()
+        c_n = nrm[:, :, None, :].expand(-1, -1, k, -1).reshape(B, 3, k * N).contiguous()
+        ppf = ref.spherical_ppf_forward(torch.gather(xyz, 2, gi), c_xyz, torch.gather(nrm, 2, gi), c_n)
+        nc = xyz - xyz.mean(2, keepdim=True)
+        if wl["voxel_shape"] == "spherical":
+            nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values + 1e-20)
+            avg, ind, cnt = ref.spherical_avg_voxelize_forward(f, nc.contiguous(), r)
+            dv, _, _ = ref.spherical_trilinear_devoxelize_forward(r, True, nc.contiguous(), avg, ind)
+        else:
+            nc = torch.clamp((nc + 1) / 2.0 * r, 0, r - 1)
+            avg, ind, cnt = ref.avg_voxelize_forward(f, torch.round(nc).to(torch.int32).contiguous(), r)
+            dv, _, _ = ref.trilinear_devoxelize_forward(r, True, nc.contiguous(), avg)
+        mask = ind == -1                                                                   # pvconv.py:68-90
+        it = ind.clone(); it[mask] = 0
+        centre = avg.gather(2, it.unsqueeze(1).expand(-1, C, -1).long())
+        rel = f - centre
+        rel[mask.unsqueeze(1).expand(-1, C, -1)] = 0
+        edge = torch.cat((rel, f), 1)
+        if host:
+            for name, t in (("ppf", ppf), ("devox", dv), ("edge", edge)):
+                if name not in out_h:
+                    out_h[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                out_h[name].copy_(t, non_blocking=True)
+            torch.cuda.synchronize()
+
+    d_p, d_f = hp.to(dev), hf.to(dev)
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(False)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    for _ in range(3):
+        step(True)
+    n2 = max(1, min(args.steps, 50))
+    t0 = time.perf_counter()
+    for _ in range(n2):
+        step(True)
+    ms2 = (time.perf_counter() - t0) * 1e3
+    value = B * N * args.steps / (ms * 1e-3)
+    base.update({
+        "value": value, "ms_per_step": ms / args.steps,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
+                         "sample": "the reference's own CUDA kernels (oracle/_ref, unmodified sources recompiled for "
+                                   "sm_100a) on the same B200 — the reference has no CPU implementation of this path"},
+        "e2e": {"value": B * N * n2 / (ms2 * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": hp.numel() * 4 + hf.numel() * 4,
+                "d2h_bytes_per_step": sum(t.numel() * 4 for t in out_h.values()), "steps": n2,
+                "ms_per_step": ms2 / n2}})
+    print(json.dumps(base))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cu_dg")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world, local)
+        return
+    from ri_b200 import shard
+    rank, world, local = shard.init_from_env()
+    try:
+        run_ours(args, rank, world, local)
+    finally:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+/*
+ * ri_b200.h — C ABI of libri_b200.so: the B200 (sm_100a) implementation of the data-parallel front end of the
+ * rotation-invariant PVCNN feature extractor.
+ *
+ * This is the drop-in boundary.  Each entry point replaces one function of the reference's pybind11 module
+ * `_multi_shape_pvcnn_backend` (/root/reference/PVCNN/modules/functional/src/bindings.cpp:13-56) or, for the
+ * matcher and the edge gather, the Python block cited beside it.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference adds in PVCNN/modules/functional/backend.py.
+ *
+ * Conventions (all entry points):
+ *   - plain device pointers + sizes; tensors are contiguous, channel-major [B, C, N] (points innermost), fp32 / int32;
+ *   - the CALLER allocates every output and the workspace; nothing is allocated or freed inside;
+ *   - the caller has made the right device current and passes its stream (`cudaStream_t` as void*); every kernel is
+ *     enqueued on that stream and the call returns without synchronising;
+ *   - return value: 0 on success, a positive cudaError_t if a launch failed, or a negative RI_ERR_* code for a bad
+ *     argument.  Never calls exit() (the reference's CUDA_CHECK_ERRORS does, cuda_utils.cuh:28-37);
+ *   - re-entrant, no global state besides a cached SM count.
+ */
+#ifndef RI_B200_H
+#define RI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RI_OK 0
+#define RI_ERR_BAD_ARG (-1)
+#define RI_ERR_WORKSPACE (-2)
+#define RI_ERR_UNSUPPORTED (-3)
+
+/* ABI version of this header/library pair. */
+int ri_abi_version(void);
+
+/* ---- k-nearest neighbours -------------------------------------------------------------------------------
+ * One direction of knn_forward_cuda (knn/knn.cpp:6-25 -> KnnKernel knn/knn.cu:5-49): for each of the n points of
+ * xyz1 [B,c,n] its k nearest (squared L2) among the m points of xyz2 [B,c,m].
+ * dist1 [B,k,n] ascending along k, idx1 [B,k,n] indices into xyz2; unfilled slots are (10000.0f, 0).
+ * Bit-exact against the reference incl. its tie rule (lower reference index first). */
+int ri_knn_f32(const float* xyz1, const float* xyz2, int B, int c, int n, int m, int k,
+               float* dist1, int* idx1, void* stream);
+
+/* knn_forward_cuda itself: both directions (knn/knn.cu:81-87). dist2/idx2 are [B,k,m]. */
+int ri_knn_bilateral_f32(const float* xyz1, const float* xyz2, int B, int c, int n, int m, int k,
+                         float* dist1, float* dist2, int* idx1, int* idx2, void* stream);
+
+/* knn_backward_cuda (knn/knn.cpp:27-52 -> KnnGradKernel knn/knn.cu:52-78), both directions.
+ * gradxyz1 [B,c,n] and gradxyz2 [B,c,m] are overwritten. */
+int ri_knn_backward_f32(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                        const int* idx1, const int* idx2, int B, int c, int n, int m, int k,
+                        float* gradxyz1, float* gradxyz2, void* stream);
+
+/* ---- point-pair features --------------------------------------------------------------------------------
+ * spherical_ppf_forward (spherical_ppf/ppf.cpp:17-36 -> spherical_ppf_kernel ppf.cu:19-92), backend argument
+ * order: coords = the points, center = the centres (functional/ppf.py:22 swaps the user-facing order).
+ * All inputs [B,3,L]; feat [B,4,L] = (angle(d,n_c), angle(d,n_p), angle(n_c,n_p), ||d||), d = center - coords. */
+int ri_ppf_f32(const float* coords, const float* center, const float* normals, const float* center_normal,
+               int B, int L, float* feat, void* stream);
+
+/* Fused neighbour gather + PPF for k-NN neighbourhoods: xyz, normals [B,3,N], idx [B,k,N] -> out [B,4,k,N];
+ * centre = point i, point = neighbour idx[b,s,i].  Equals ri_ppf_f32 on the gathered/expanded columns. */
+int ri_ppf_gather_f32(const float* xyz, const float* normals, const int* idx, int B, int N, int k,
+                      float* out, void* stream);
+
+/* ---- voxelization ---------------------------------------------------------------------------------------
+ * spherical_avg_voxelize_forward (spherical_voxelization/spherical_vox.cpp:17-46) and avg_voxelize_forward
+ * (voxelization/vox.cpp:17-43).  feat [B,C,N]; coords [B,3,N] (fp32 normalised Cartesian for the spherical
+ * variant, int32 voxel coordinates for the cube variant) -> out [B,C,r^3], ind [B,N] (-1 = undefined point),
+ * cnt [B,r^3].  All three outputs are fully overwritten (no pre-zeroing needed).
+ * workspace >= ri_voxelize_workspace_bytes(B, N, r) bytes of device memory, 16-byte aligned. */
+size_t ri_voxelize_workspace_bytes(int B, int N, int r);
+int ri_sph_voxelize_f32(const float* feat, const float* coords, int B, int C, int N, int r,
+                        float* out, int* ind, int* cnt, void* workspace, size_t workspace_bytes, void* stream);
+int ri_cube_voxelize_f32(const float* feat, const int* coords, int B, int C, int N, int r,
+                         float* out, int* ind, int* cnt, void* workspace, size_t workspace_bytes, void* stream);
+
+/* avg_voxelize_backward == spherical_avg_voxelize_backward (vox.cpp:54-78, vox.cu:87-111):
+ * grad_x [B,C,N] = grad_y[b,c,ind] / cnt (0 for undefined points); grad_x fully overwritten. */
+int ri_voxelize_backward_f32(const float* grad_y, const int* ind, const int* cnt, int B, int C, int N, int s,
+                             float* grad_x, void* stream);
+
+/* ---- devoxelization -------------------------------------------------------------------------------------
+ * trilinear_devoxelize_forward (interpolate/trilinear_devox.cpp:18-55): coords [B,3,N] in grid units [0,r-1],
+ * feat [B,C,r^3] -> outs [B,C,N], inds [B,8,N], wgts [B,8,N] (all fully overwritten). */
+int ri_trilinear_devox_f32(const float* coords, const float* feat, int B, int C, int N, int r,
+                           float* outs, int* inds, float* wgts, void* stream);
+
+/* spherical_trilinear_devoxelize_forward (interpolate/spherical_trilinear_devox.cpp:19-56), index quirks kept.
+ * coords = normalised Cartesian coords, g_inds [B,N] = spherical cell of each point. Requires r >= 4. */
+int ri_sph_trilinear_devox_f32(const float* coords, const float* feat, const int* g_inds, int B, int C, int N, int r,
+                               float* outs, int* inds, float* wgts, void* stream);
+
+/* trilinear_devoxelize_backward / spherical_trilinear_devoxelize_backward (trilinear_devox.cu:120-163,
+ * spherical_trilinear_devox.cu:150-194): grad_x [B,C,s] fully overwritten; skip_undefined != 0 skips points whose
+ * inds[b,0,i] == -1 (the spherical variant). */
+int ri_devox_backward_f32(const float* grad_y, const int* inds, const float* wgts, int B, int C, int N, int s,
+                          int skip_undefined, float* grad_x, void* stream);
+
+/* ---- DGCNN voxel-neighbour edge features (PVCNN/modules/pvconv.py:68-90) --------------------------------
+ * avg [B,C,s], feat [B,C,N], inds [B,N] -> out [B,2C,N] = cat(feat - avg[:, :, inds] (0 where inds == -1), feat). */
+int ri_voxel_edge_gather_f32(const float* avg, const float* feat, const int* inds, int B, int C, int N, int s,
+                             float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RI_B200_H */

@@ -1,0 +1,231 @@
+"""ctypes front end of oracle/ri_oracle.c — TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may import
+this module.  The product package (ri_b200) never does; it fails loudly when its CUDA library is missing.
+
+Each wrapper takes/returns C-contiguous numpy arrays with the reference's layouts ([B,C,N], points
+innermost) and cites the reference code the C function restates (paths relative to /root/reference).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "ri_oracle.c")
+LIB = os.path.join(HERE, "libri_oracle.so")
+
+_lib = None
+
+
+def build(force=False):
+    """gcc -O2 -ffp-contract=off: the C file spells every fma itself, the compiler must add none."""
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-std=c11", "-ffp-contract=off",
+                               "-fno-fast-math", "-fopenmp", SRC, "-o", LIB, "-lm"])
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+    return _lib
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def knn(xyz1, xyz2, k):
+    """Bilateral kNN as knn_forward_cuda does (knn/knn.cpp:6-25, knn/knn.cu:81-87): returns
+    dist1[B,k,n], dist2[B,k,m], idx1, idx2."""
+    xyz1, xyz2 = _f(xyz1), _f(xyz2)
+    B, c, n = xyz1.shape
+    m = xyz2.shape[2]
+    d1 = np.empty((B, k, n), np.float32); i1 = np.empty((B, k, n), np.int32)
+    d2 = np.empty((B, k, m), np.float32); i2 = np.empty((B, k, m), np.int32)
+    lib().ri_oracle_knn(_p(xyz1), _p(xyz2), B, c, n, m, k, _p(d1), _p(i1))
+    lib().ri_oracle_knn(_p(xyz2), _p(xyz1), B, c, m, n, k, _p(d2), _p(i2))
+    return d1, d2, i1, i2
+
+
+def knn_one(xyz1, xyz2, k):
+    """One direction only (queries xyz1, references xyz2)."""
+    xyz1, xyz2 = _f(xyz1), _f(xyz2)
+    B, c, n = xyz1.shape
+    m = xyz2.shape[2]
+    d1 = np.empty((B, k, n), np.float32); i1 = np.empty((B, k, n), np.int32)
+    lib().ri_oracle_knn(_p(xyz1), _p(xyz2), B, c, n, m, k, _p(d1), _p(i1))
+    return d1, i1
+
+
+def knn_grad(xyz1, xyz2, gd1, gd2, idx1, idx2):
+    """knn_backward_cuda (knn/knn.cpp:27-52, knn/knn.cu:89-97)."""
+    xyz1, xyz2, gd1, gd2, idx1, idx2 = _f(xyz1), _f(xyz2), _f(gd1), _f(gd2), _i(idx1), _i(idx2)
+    B, c, n = xyz1.shape
+    m = xyz2.shape[2]
+    k = idx1.shape[1]
+    g1 = np.zeros((B, c, n), np.float32); g2 = np.zeros((B, c, m), np.float32)
+    lib().ri_oracle_knn_grad(_p(xyz1), _p(xyz2), _p(gd1), _p(idx1), B, c, n, m, k, _p(g1), _p(g2))
+    lib().ri_oracle_knn_grad(_p(xyz2), _p(xyz1), _p(gd2), _p(idx2), B, c, m, n, k, _p(g2), _p(g1))
+    return g1, g2
+
+
+def ppf_backend(coords, center, normals, center_normal):
+    """_backend.spherical_ppf_forward argument order (spherical_ppf/ppf.cpp:17-36)."""
+    coords, center, normals, center_normal = _f(coords), _f(center), _f(normals), _f(center_normal)
+    B, _, L = coords.shape
+    feat = np.zeros((B, 4, L), np.float32)
+    lib().ri_oracle_ppf(_p(coords), _p(center), _p(normals), _p(center_normal), B, L, _p(feat))
+    return feat
+
+
+def ppf(centers_coords, points_coords, centers_normals, points_normals):
+    """functional/ppf.py:8-22 — note the argument swap on the way to the backend (ppf.py:22)."""
+    return ppf_backend(points_coords, centers_coords, points_normals, centers_normals)
+
+
+def sph_grid_stats(coords, r):
+    coords = _f(coords)
+    B, _, N = coords.shape
+    ind = np.empty((B, N), np.int32); cnt = np.empty((B, r ** 3), np.int32)
+    lib().ri_oracle_sph_grid_stats(_p(coords), B, N, r, _p(ind), _p(cnt))
+    return ind, cnt
+
+
+def sph_grid_cont(coords, r):
+    coords = _f(coords)
+    B, _, N = coords.shape
+    gc = np.empty((B, N, 3), np.float64)
+    lib().ri_oracle_sph_grid_cont(_p(coords), B, N, r, _p(gc))
+    return gc
+
+
+def cube_grid_stats(vox_coords, r):
+    vox_coords = _i(vox_coords)
+    B, _, N = vox_coords.shape
+    ind = np.empty((B, N), np.int32); cnt = np.empty((B, r ** 3), np.int32)
+    lib().ri_oracle_cube_grid_stats(_p(vox_coords), B, N, r, _p(ind), _p(cnt))
+    return ind, cnt
+
+
+def scatter_mean(features, ind, cnt, r):
+    features, ind, cnt = _f(features), _i(ind), _i(cnt)
+    B, C, N = features.shape
+    s = r ** 3
+    out = np.empty((B, C, s), np.float32)
+    lib().ri_oracle_avg_voxelize(_p(features), _p(ind), _p(cnt), B, C, N, s, _p(out))
+    return out
+
+
+def spherical_avg_voxelize(features, coords, r):
+    """_backend.spherical_avg_voxelize_forward (spherical_voxelization/spherical_vox.cpp:17-46): (out, ind, cnt)."""
+    ind, cnt = sph_grid_stats(coords, r)
+    return scatter_mean(features, ind, cnt, r), ind, cnt
+
+
+def avg_voxelize(features, vox_coords, r):
+    """_backend.avg_voxelize_forward (voxelization/vox.cpp:17-43): (out, ind, cnt)."""
+    ind, cnt = cube_grid_stats(vox_coords, r)
+    return scatter_mean(features, ind, cnt, r), ind, cnt
+
+
+def avg_voxelize_grad(grad_y, ind, cnt):
+    """avg_voxelize_backward == spherical_avg_voxelize_backward (vox.cpp:54-78)."""
+    grad_y, ind, cnt = _f(grad_y), _i(ind), _i(cnt)
+    B, C, s = grad_y.shape
+    N = ind.shape[1]
+    gx = np.empty((B, C, N), np.float32)
+    lib().ri_oracle_avg_voxelize_grad(_p(grad_y), _p(ind), _p(cnt), B, C, N, s, _p(gx))
+    return gx
+
+
+def trilinear_devoxelize(coords, features, r):
+    """_backend.trilinear_devoxelize_forward (interpolate/trilinear_devox.cpp:18-55): (outs, inds, wgts)."""
+    coords, features = _f(coords), _f(features)
+    B, C = features.shape[:2]
+    features = features.reshape(B, C, -1)
+    N = coords.shape[2]
+    outs = np.empty((B, C, N), np.float32); inds = np.empty((B, 8, N), np.int32); wgts = np.empty((B, 8, N), np.float32)
+    lib().ri_oracle_trilinear_devox(_p(coords), _p(features), B, C, N, r, _p(outs), _p(inds), _p(wgts))
+    return outs, inds, wgts
+
+
+def spherical_trilinear_devoxelize(coords, features, g_inds, r):
+    """_backend.spherical_trilinear_devoxelize_forward (interpolate/spherical_trilinear_devox.cpp:19-56)."""
+    coords, features, g_inds = _f(coords), _f(features), _i(g_inds)
+    B, C = features.shape[:2]
+    features = features.reshape(B, C, -1)
+    N = coords.shape[2]
+    outs = np.empty((B, C, N), np.float32); inds = np.empty((B, 8, N), np.int32); wgts = np.empty((B, 8, N), np.float32)
+    lib().ri_oracle_sph_trilinear_devox(_p(coords), _p(features), _p(g_inds), B, C, N, r, _p(outs), _p(inds), _p(wgts))
+    return outs, inds, wgts
+
+
+def devox_grad(grad_y, inds, wgts, r, spherical):
+    grad_y, inds, wgts = _f(grad_y), _i(inds), _f(wgts)
+    B, C, N = grad_y.shape
+    s = r ** 3
+    gx = np.empty((B, C, s), np.float32)
+    lib().ri_oracle_devox_grad(_p(grad_y), _p(inds), _p(wgts), B, C, N, s, int(bool(spherical)), _p(gx))
+    return gx
+
+
+def voxel_edge_gather(avg, features, inds):
+    """PVCNN/modules/pvconv.py:68-90 -> [B,2C,N]."""
+    features, inds = _f(features), _i(inds)
+    B, C, N = features.shape
+    avg = _f(avg).reshape(B, C, -1)
+    s = avg.shape[2]
+    out = np.empty((B, 2 * C, N), np.float32)
+    lib().ri_oracle_voxel_edge_gather(_p(avg), _p(features), _p(inds), B, C, N, s, _p(out))
+    return out
+
+
+def find_correspondence_one_pair(feat1, feat2):
+    """datasets/deepgmr_mn40.py:232-244, restated with the same numpy calls (fp32 in, fp32 sgemm)."""
+    diff = (np.power(np.linalg.norm(feat1, axis=1, keepdims=True), 2)
+            + np.power(np.linalg.norm(feat2, axis=1, keepdims=True).T, 2)
+            - 2 * np.dot(feat1, feat2.T))
+    c1 = np.argmin(diff, axis=1)
+    c2 = np.argmin(diff, axis=0)
+    mask = (c2[c1] == np.arange(c1.shape[0]))
+    return np.arange(c1.shape[0])[mask], c1[mask], diff
+
+
+# ---- module-level prologues (torch-free numpy restatements; fp32 throughout) -------------------------
+
+def spherical_voxelization_module(features, coords, r):
+    """Spherical_Voxelization.forward (PVCNN/modules/spherical_vox.py:14-23).  NOTE: numpy's mean/norm
+    reductions are not bit-identical to torch's; parity tests feed the SAME norm_coords to both sides."""
+    coords = _f(coords)
+    nc = coords - coords.mean(2, keepdims=True, dtype=np.float32)
+    nrm = np.sqrt((nc * nc).sum(1, keepdims=True, dtype=np.float32)).max(2, keepdims=True)
+    nc = (nc / (nrm + np.float32(1e-20))).astype(np.float32)
+    out, ind, _ = spherical_avg_voxelize(features, nc, r)
+    return out, ind, nc
+
+
+def voxelization_module(features, coords, r, normalize=True, eps=0.0):
+    """Voxelization.forward (PVCNN/modules/voxelization.py:16-35)."""
+    coords = _f(coords)
+    nc = coords - coords.mean(2, keepdims=True, dtype=np.float32)
+    if normalize:
+        nrm = np.sqrt((nc * nc).sum(1, keepdims=True, dtype=np.float32)).max(2, keepdims=True)
+        nc = nc / (nrm * np.float32(2.0) + np.float32(eps)) + np.float32(0.5)
+    else:
+        nc = (nc + np.float32(1)) / np.float32(2.0)
+    nc = np.clip(nc * np.float32(r), 0, r - 1).astype(np.float32)
+    vox = np.rint(nc).astype(np.int32)                     # torch.round == half-to-even == rint
+    out, ind, _ = avg_voxelize(features, vox, r)
+    return out, ind, nc

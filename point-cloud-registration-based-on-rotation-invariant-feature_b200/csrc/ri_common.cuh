@@ -1,0 +1,138 @@
+// ri_common.cuh — shared device helpers for the sm_100a kernels behind include/ri_b200.h.
+//
+// Arithmetic pins.  Where the contract is bit-exactness against the reference kernels (voxel indices,
+// counts, KNN order, devox corner indices) the fp32/fp64 operation ORDER is spelled with explicit
+// round-to-nearest intrinsics (__fmaf_rn, __fmul_rn, __fdiv_rn, __fsqrt_rn, __dadd_rn ...), so it cannot
+// drift with compiler flags or contraction heuristics.  The order itself was read from the sm_100a PTX of
+// the reference sources (/root/reference/PVCNN/modules/functional/src/**); each helper cites the lines.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define RI_OK 0
+#define RI_ERR_BAD_ARG (-1)
+#define RI_ERR_WORKSPACE (-2)
+#define RI_ERR_UNSUPPORTED (-3)
+
+#define RI_SM_COUNT_FALLBACK 148
+
+// acos(-1.0) as the reference evaluates it on the device (`#define PI acos(-1.0)`,
+// spherical_voxelization/spherical_vox.cu:5): the inlined f64 acos returns 0x400921FB54442D18 == M_PI.
+#define RI_PI 3.14159265358979311600e+00
+
+#define RI_LAUNCH_CHECK()                                   \
+    do {                                                    \
+        cudaError_t e__ = cudaGetLastError();               \
+        if (e__ != cudaSuccess) return (int)e__;            \
+    } while (0)
+
+static inline int ri_num_sms()
+{
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = RI_SM_COUNT_FALLBACK;
+        cached = n;
+    }
+    return cached;
+}
+
+// x*x' + y*y' + z*z' as nvcc contracts it for the reference: fma(z,z', fma(x,x', y*y')).
+// (PTX of ppf.cu:56-83 and spherical_vox.cu:37: mul.f32 on the y term, then two fma.rn.f32.)
+__device__ __forceinline__ float ri_dot3(float ax, float ay, float az, float bx, float by, float bz)
+{
+    return __fmaf_rn(az, bz, __fmaf_rn(ax, bx, __fmul_rn(ay, by)));
+}
+
+// Spherical coordinates of a normalised point, exactly as spherical_vox.cu:34-56 and
+// spherical_trilinear_devox.cu:48-65 evaluate them (mixed f32/f64, libdevice acosf/atanf).
+// Returns false for an "undefined" point (ind = -1).
+__device__ __forceinline__ bool ri_sph_coords(float x, float y, float z, int r,
+                                              float& gama, float& alpha, float& beta)
+{
+    gama = __fsqrt_rn(ri_dot3(x, y, z, x, y, z));
+    if (gama == 0.0f || gama >= 1.0f) return false;
+    const float t = __fdiv_rn(z, gama);
+    if (t > 1.0f || t < -1.0f) return false;
+    beta = acosf(t);
+    if ((double)beta >= RI_PI) return false;
+    if (x == 0.0f && y != 0.0f) {
+        alpha = __double2float_rn(__dmul_rn(__dmul_rn((double)__fdiv_rn(y, fabsf(y)), RI_PI), 0.5));
+    } else if (x == 0.0f && y == 0.0f) {
+        alpha = 0.0f;
+    } else {
+        const float sgn = __fsub_rn(1.0f, __fdiv_rn(x, fabsf(x)));
+        alpha = __double2float_rn(__fma_rn(__dmul_rn(RI_PI, (double)sgn), 0.5, (double)atanf(__fdiv_rn(y, x))));
+    }
+    alpha = __double2float_rn(__dadd_rn(__ddiv_rn(RI_PI, (double)r), (double)alpha));
+    if (alpha < 0.0f) alpha = __double2float_rn(__fma_rn(RI_PI, 2.0, (double)alpha));
+    return true;
+}
+
+// Spherical cell of a point: spherical_vox.cu:59-65.  -1 if undefined.
+__device__ __forceinline__ int ri_sph_cell(float x, float y, float z, int r)
+{
+    float g, a, be;
+    if (!ri_sph_coords(x, y, z, r, g, a, be)) return -1;
+    const float rf = (float)r;
+    int gx = (int)floorf(__fmul_rn(g, rf));
+    int gy = (int)floor(__ddiv_rn((double)__fmul_rn(__fmul_rn(a, rf), 0.5f), RI_PI));
+    int gz = (int)floor(__ddiv_rn((double)__fmul_rn(be, rf), RI_PI));
+    gx = gx >= r ? r - 1 : gx;
+    gy = gy >= r ? r - 1 : gy;
+    gz = gz >= r ? r - 1 : gz;
+    return gx * r * r + gy * r + gz;
+}
+
+// Corner weights / indices shared by both devoxelizers (interpolate/trilinear_devox.cu:46-76).
+__device__ __forceinline__ void ri_corners(float d1a, float d1b, float d1c, int lo_a, int lo_b, int lo_c,
+                                           int r, int r2, int (&id)[8], float (&w)[8])
+{
+    const float d0a = __fsub_rn(1.0f, d1a), d0b = __fsub_rn(1.0f, d1b), d0c = __fsub_rn(1.0f, d1c);
+    const float w00 = __fmul_rn(d0a, d0b), w01 = __fmul_rn(d0a, d1b);
+    const float w10 = __fmul_rn(d1a, d0b), w11 = __fmul_rn(d1a, d1b);
+    w[0] = __fmul_rn(w00, d0c); w[1] = __fmul_rn(w00, d1c);
+    w[2] = __fmul_rn(w01, d0c); w[3] = __fmul_rn(w01, d1c);
+    w[4] = __fmul_rn(w10, d0c); w[5] = __fmul_rn(w10, d1c);
+    w[6] = __fmul_rn(w11, d0c); w[7] = __fmul_rn(w11, d1c);
+    const int ha = d1a > 0.0f ? r2 : 0, hb = d1b > 0.0f ? r : 0, hc = d1c > 0.0f ? 1 : 0;
+    id[0] = lo_a * r2 + lo_b * r + lo_c;
+    id[1] = id[0] + hc;
+    id[2] = id[0] + hb;
+    id[3] = id[2] + hc;
+    id[4] = id[0] + ha;
+    id[5] = id[4] + hc;
+    id[6] = id[4] + hb;
+    id[7] = id[6] + hc;
+}
+
+// ---- PTX wrappers: bulk async copy (TMA engine, SASS UBLKCP) and proxy fence -------------------------
+__device__ __forceinline__ uint32_t ri_smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void ri_fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void ri_bulk_store(void* gdst, const void* ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(ri_smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ri_bulk_commit()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void ri_bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void ri_bulk_wait()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory");
+}

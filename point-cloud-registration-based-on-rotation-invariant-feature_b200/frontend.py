@@ -1,0 +1,195 @@
+"""FrontEnd — the data-parallel front end of the rotation-invariant PVCNN feature extractor as ONE engine.
+
+One "step" takes a batch of clouds (xyz | normal, [B,6,N]) and their per-point input features ([B,C,N]) and
+produces everything the dense layers of a PVConv block consume (SURVEY.md §3 call stack A, §8 rows a1-a10):
+
+    branch A (ALU bound)      k-NN self query  ->  fused neighbour gather + PPF          -> ppf   [B,4,k,N]
+    branch B (HBM bound)      coordinate prologue (torch, defines the bits) -> voxelize  -> grid  [B,C,r,r,r], ind, cnt
+                              -> trilinear devoxelize of the grid                        -> devox [B,C,N]
+                              -> DGCNN voxel-neighbour edge features                     -> edge  [B,2C,N]
+
+The two branches are independent, so they run on two streams inside one captured CUDA graph: the brute-force
+k-NN (register/ALU bound) overlaps the dense grid write (HBM bound).  All buffers are allocated once; the kernels
+are enqueued straight through the C ABI (no per-op allocation, no dispatcher overhead) and replayed as a graph.
+
+`forward()`          runs one step on the device-resident input buffers (what bench.py's `value` times).
+`__call__(pts, feats)`  is the host-facing call: pinned host inputs -> H2D -> step -> D2H of the per-point
+                        outputs into pinned host buffers (what bench.py's `e2e` times).
+"""
+import torch
+
+from . import _lib
+
+_L = _lib.lib
+_check = _lib.check
+
+
+class FrontEnd:
+    KERNELS_PER_STEP = 6     # knn, ppf_gather, vox_prepare, vox_fill, devox, edge_gather (this package's own kernels)
+
+    def __init__(self, B, N, C, k=20, r=32, voxel_shape='spherical', normalize=False, eps=0.0,
+                 device='cuda', use_graph=True, overlap=True):
+        if voxel_shape not in ('spherical', 'cube'):
+            raise ValueError('voxel_shape must be "spherical" or "cube"')
+        self.B, self.N, self.C, self.k, self.r = int(B), int(N), int(C), int(k), int(r)
+        self.voxel_shape, self.normalize, self.eps = voxel_shape, normalize, eps
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('FrontEnd runs on a CUDA device only (no CPU path exists)')
+        self.use_graph, self.overlap = use_graph, overlap
+        B, N, C, k, r = self.B, self.N, self.C, self.k, self.r
+        s = r ** 3
+        f32, i32, dev = torch.float32, torch.int32, self.device
+        with torch.cuda.device(dev):
+            # inputs
+            self.points = torch.zeros((B, 6, N), dtype=f32, device=dev)
+            self.features = torch.zeros((B, C, N), dtype=f32, device=dev)
+            # branch A
+            self.knn_dist = torch.empty((B, k, N), dtype=f32, device=dev)
+            self.knn_idx = torch.empty((B, k, N), dtype=i32, device=dev)
+            self.ppf = torch.empty((B, 4, k, N), dtype=f32, device=dev)
+            # branch B
+            self.grid = torch.empty((B, C, r, r, r), dtype=f32, device=dev)
+            self.ind = torch.empty((B, N), dtype=i32, device=dev)
+            self.cnt = torch.empty((B, s), dtype=i32, device=dev)
+            self.devox = torch.empty((B, C, N), dtype=f32, device=dev)
+            self.devox_inds = torch.empty((B, 8, N), dtype=i32, device=dev)
+            self.devox_wgts = torch.empty((B, 8, N), dtype=f32, device=dev)
+            self.edge = torch.empty((B, 2 * C, N), dtype=f32, device=dev)
+            self._ws_bytes = _L.ri_voxelize_workspace_bytes(B, N, r)
+            self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=dev)
+            self._side = torch.cuda.Stream(device=dev)
+            # host staging (pinned)
+            self.h_points = torch.empty((B, 6, N), dtype=f32).pin_memory()
+            self.h_features = torch.empty((B, C, N), dtype=f32).pin_memory()
+            self.h_ppf = torch.empty((B, 4, k, N), dtype=f32).pin_memory()
+            self.h_devox = torch.empty((B, C, N), dtype=f32).pin_memory()
+            self.h_edge = torch.empty((B, 2 * C, N), dtype=f32).pin_memory()
+        self._graph = None
+        self.norm_coords = None
+
+    # bytes moved per host-facing call
+    @property
+    def h2d_bytes(self):
+        return self.h_points.numel() * 4 + self.h_features.numel() * 4
+
+    @property
+    def d2h_bytes(self):
+        return (self.h_ppf.numel() + self.h_devox.numel() + self.h_edge.numel()) * 4
+
+    # ------------------------------------------------------------------ the step, enqueued on current stream(s)
+    def _branch_a(self):
+        st = torch.cuda.current_stream().cuda_stream
+        B, N, k = self.B, self.N, self.k
+        xyz = self._xyz
+        _check(_L.ri_knn_f32(xyz.data_ptr(), xyz.data_ptr(), B, 3, N, N, k,
+                             self.knn_dist.data_ptr(), self.knn_idx.data_ptr(), st), 'ri_knn')
+        _check(_L.ri_ppf_gather_f32(xyz.data_ptr(), self._nrm.data_ptr(), self.knn_idx.data_ptr(), B, N, k,
+                                    self.ppf.data_ptr(), st), 'ri_ppf_gather')
+
+    def _branch_b(self):
+        st = torch.cuda.current_stream().cuda_stream
+        B, N, C, r = self.B, self.N, self.C, self.r
+        coords = self._xyz
+        # coordinate prologue: torch ops, exactly the module shells (modules/voxelization.py), because these
+        # reductions define the bits the binning kernel must see.
+        nc = coords - coords.mean(2, keepdim=True)
+        if self.voxel_shape == 'spherical':
+            nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values + 1e-20)
+            self.norm_coords = nc
+            _check(_L.ri_sph_voxelize_f32(self.features.data_ptr(), nc.data_ptr(), B, C, N, r,
+                                          self.grid.data_ptr(), self.ind.data_ptr(), self.cnt.data_ptr(),
+                                          self._ws.data_ptr(), self._ws_bytes, st), 'ri_sph_voxelize')
+            _check(_L.ri_sph_trilinear_devox_f32(nc.data_ptr(), self.grid.data_ptr(), self.ind.data_ptr(), B, C, N, r,
+                                                 self.devox.data_ptr(), self.devox_inds.data_ptr(),
+                                                 self.devox_wgts.data_ptr(), st), 'ri_sph_trilinear_devox')
+        else:
+            if self.normalize:
+                nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + self.eps) + 0.5
+            else:
+                nc = (nc + 1) / 2.0
+            nc = torch.clamp(nc * r, 0, r - 1)
+            vox = torch.round(nc).to(torch.int32)
+            self.norm_coords = nc
+            self._vox_coords = vox
+            _check(_L.ri_cube_voxelize_f32(self.features.data_ptr(), vox.data_ptr(), B, C, N, r,
+                                           self.grid.data_ptr(), self.ind.data_ptr(), self.cnt.data_ptr(),
+                                           self._ws.data_ptr(), self._ws_bytes, st), 'ri_cube_voxelize')
+            _check(_L.ri_trilinear_devox_f32(nc.data_ptr(), self.grid.data_ptr(), B, C, N, r,
+                                             self.devox.data_ptr(), self.devox_inds.data_ptr(),
+                                             self.devox_wgts.data_ptr(), st), 'ri_trilinear_devox')
+        _check(_L.ri_voxel_edge_gather_f32(self.grid.data_ptr(), self.features.data_ptr(), self.ind.data_ptr(),
+                                           B, C, N, r ** 3, self.edge.data_ptr(), st), 'ri_voxel_edge_gather')
+
+    def _step(self):
+        self._xyz = self.points[:, :3, :].contiguous()
+        self._nrm = self.points[:, 3:6, :].contiguous()
+        if self.overlap:
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self._branch_a()
+            self._branch_b()
+            main.wait_stream(self._side)
+        else:
+            self._branch_a()
+            self._branch_b()
+
+    def _capture(self):
+        with torch.cuda.device(self.device):
+            warm = torch.cuda.Stream(device=self.device)
+            warm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(warm):
+                for _ in range(2):
+                    self._step()
+            torch.cuda.current_stream().wait_stream(warm)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._step()
+            self._graph = g
+
+    def forward(self):
+        """One step on the device-resident `points` / `features` buffers (asynchronous)."""
+        with torch.cuda.device(self.device):
+            if not self.use_graph:
+                self._step()
+                return
+            if self._graph is None:
+                self._capture()
+            self._graph.replay()
+
+    def load(self, points, features):
+        """Copy a batch ([B,6,N], [B,C,N]; numpy or torch, host or device) into the device input buffers."""
+        self.points.copy_(torch.as_tensor(points), non_blocking=True)
+        self.features.copy_(torch.as_tensor(features), non_blocking=True)
+
+    def __call__(self, points_host, features_host):
+        """Host-facing call: host arrays in, pinned host tensors out {ppf, devox, edge} (synchronous)."""
+        with torch.cuda.device(self.device):
+            self.h_points.copy_(torch.as_tensor(points_host))
+            self.h_features.copy_(torch.as_tensor(features_host))
+            return self.run_staged()
+
+    def run_staged(self):
+        """H2D from the pinned staging buffers -> step -> D2H into pinned buffers, then wait."""
+        with torch.cuda.device(self.device):
+            self.points.copy_(self.h_points, non_blocking=True)
+            self.features.copy_(self.h_features, non_blocking=True)
+            self.forward()
+            self.h_ppf.copy_(self.ppf, non_blocking=True)
+            self.h_devox.copy_(self.devox, non_blocking=True)
+            self.h_edge.copy_(self.edge, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return {'ppf': self.h_ppf, 'devox': self.h_devox, 'edge': self.h_edge}
+
+    # algorithmic (compulsory) bytes of one step, SURVEY.md §8(d) formulas, fused KNN->PPF form
+    def algorithmic_bytes(self):
+        B, N, C, k, r = self.B, self.N, self.C, self.k, self.r
+        s = r ** 3
+        knn_ppf = 24 * N + 16 * k * N
+        vox = 12 * N + 4 * C * N + 4 * N + 4 * s + 4 * C * s
+        devox = 12 * N + 4 * N + min(32 * C * N, 4 * C * s) + 4 * C * N + 64 * N
+        edge = 4 * N + 4 * C * N + 4 * C * N + 8 * C * N
+        return {'knn_ppf': B * knn_ppf, 'voxelize': B * vox, 'devox': B * devox, 'edge': B * edge,
+                'total': B * (knn_ppf + vox + devox + edge)}

@@ -1,0 +1,281 @@
+"""GPU parity tests: the sm_100a kernels (through torch.ops.ri.* -> the C ABI) against
+  (1) the reference's own CUDA kernels recompiled for sm_100a (oracle/_ref, live, same device tensors),
+  (2) the committed golden vectors those kernels produced (tests/golden/),
+  (3) the CPU oracle (oracle/ri_oracle.c).
+Bar (north_star): voxel indices, counts, KNN indices (full order), devox corner indices bit-exact; PPF, voxel means,
+devoxelized features, distances within 1e-5 relative (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from _util import TOL, load_golden, rel_err, scaled_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ri():
+    import ri_b200
+    return ri_b200
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def A(t):
+    return t.detach().cpu().numpy()
+
+
+def clouds(B, N, seed, surface=True):
+    from ri_b200 import synth
+    return synth.make_clouds(B, N, seed=seed) if surface else np.random.default_rng(seed).standard_normal((B, 6, N)).astype(np.float32)
+
+
+def sph_norm(xyz):
+    nc = xyz - xyz.mean(2, keepdim=True)
+    return (nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values + 1e-20)).contiguous()
+
+
+# ================================================================================================ KNN
+def test_knn_golden(ri, golden_dir):
+    g = load_golden(golden_dir, "knn.npz")
+    d1, d2, i1, i2 = torch.ops.ri.knn(T(g["xyz1"]), T(g["xyz2"]), int(g["k"]))
+    assert np.array_equal(A(i1), g["idx1"]) and np.array_equal(A(i2), g["idx2"])
+    assert np.array_equal(A(d1), g["dist1"]) and np.array_equal(A(d2), g["dist2"])      # same fma chain -> same bits
+    e = load_golden(golden_dir, "knn_edge.npz")
+    d1, d2, i1, i2 = torch.ops.ri.knn(T(e["xq"]), T(e["xs"]), 8)                        # m < k
+    assert np.array_equal(A(i1), e["idx1"]) and np.array_equal(A(i2), e["idx2"])
+    assert np.array_equal(A(d1), e["dist1"]) and np.array_equal(A(d2), e["dist2"])
+    d, i = torch.ops.ri.knn_one(T(e["xc"]), T(e["xc"]), 20)
+    assert np.array_equal(A(i), e["self_idx"]) and np.array_equal(A(d), e["self_dist"])
+    d1, d2, i1, i2 = torch.ops.ri.knn(T(e["x5"]), T(e["y5"]), 4)                        # generic channel count
+    assert np.array_equal(A(i1), e["c5_idx1"]) and np.array_equal(A(i2), e["c5_idx2"])
+    assert np.array_equal(A(d1), e["c5_dist1"]) and np.array_equal(A(d2), e["c5_dist2"])
+
+
+@pytest.mark.parametrize("n,m,k", [(1024, 1024, 20), (1000, 777, 16), (33, 2100, 5), (512, 512, 32), (64, 64, 1),
+                                    (300, 300, 40)])
+def test_knn_vs_reference_and_oracle(ri, ref_backend, oracle, n, m, k):
+    B = 3
+    x1 = clouds(B, n, 1)[:, :3].copy(); x2 = clouds(B, m, 2)[:, :3].copy()
+    q = min(n, m) // 2
+    x2[:, :, :q] = x1[:, :, :q]                       # shared points: d = 0 and ties
+    x2[:, :, m - 4:] = x2[:, :, :4]                   # duplicates at the far end
+    d1, d2, i1, i2 = torch.ops.ri.knn(T(x1), T(x2), k)
+    if ref_backend is not None:
+        r1, r2, j1, j2 = ref_backend.knn_forward_cuda(T(x1), T(x2), k)
+        assert torch.equal(i1, j1) and torch.equal(i2, j2)
+        assert torch.equal(d1, r1) and torch.equal(d2, r2)
+    o1, o2, p1, p2 = oracle.knn(x1, x2, k)
+    assert np.array_equal(A(i1), p1) and np.array_equal(A(i2), p2)
+    assert np.array_equal(A(d1), o1) and np.array_equal(A(d2), o2)
+
+
+def test_knn_full_size_properties(ri):
+    """BASELINE size (32 x 1024, k = 20): size-independent properties."""
+    x = T(clouds(32, 1024, 3)[:, :3].copy())
+    d, i = torch.ops.ri.knn_one(x, x, 20)
+    assert bool((d[:, 1:] >= d[:, :-1]).all())                         # ascending along k
+    assert bool((d[:, 0] == 0).all())                                  # self (or an exact duplicate) first
+    assert int(i.min()) >= 0 and int(i.max()) < 1024
+    gathered = torch.gather(x, 2, i.reshape(32, 1, -1).expand(-1, 3, -1).long()).reshape(32, 3, 20, 1024)
+    diff = x[:, :, None, :] - gathered
+    d_re = torch.addcmul(torch.addcmul(diff[:, 0] * diff[:, 0], diff[:, 1], diff[:, 1]), diff[:, 2], diff[:, 2])
+    assert float((d_re - d).abs().max()) <= 1e-6                       # indices really are at those distances
+    full = ((x[:, :, :, None] - x[:, :, None, :]) ** 2).sum(1)
+    kth = full.kthvalue(20, dim=2).values
+    assert float((kth - d[:, 19]).abs().max()) <= 1e-5                 # k-th distance matches a dense reference
+    d2, i2 = torch.ops.ri.knn_one(x, x, 20)
+    assert torch.equal(i, i2)                                          # deterministic
+
+
+def test_knn_backward(ri, ref_backend, golden_dir):
+    g = load_golden(golden_dir, "knn.npz")
+    g1, g2 = torch.ops.ri.knn_backward(T(g["xyz1"]), T(g["xyz2"]), T(g["graddist1"]), T(g["graddist2"]),
+                                       T(g["idx1"]), T(g["idx2"]))
+    assert scaled_err(A(g1), g["gradxyz1"]) <= TOL and scaled_err(A(g2), g["gradxyz2"]) <= TOL
+
+
+# ================================================================================================ PPF
+def test_ppf_golden(ri, golden_dir, oracle):
+    g = load_golden(golden_dir, "ppf.npz")
+    f = torch.ops.ri.ppf(T(g["coords"]), T(g["center"]), T(g["normals"]), T(g["center_normal"]))
+    assert rel_err(A(f), g["feat"]) <= TOL
+    assert np.array_equal(A(f), g["feat"])           # same op order + same f64 acos => identical bits
+    o = oracle.ppf_backend(g["coords"], g["center"], g["normals"], g["center_normal"])
+    assert np.max(np.abs(o - g["feat"])) <= 1e-6      # host libm acos vs device acos: <= 1 ulp of pi
+
+
+def test_ppf_gather_equals_columns(ri, ref_backend):
+    B, N, k = 4, 1024, 20
+    pts = clouds(B, N, 5)
+    xyz, nrm = T(pts[:, :3].copy()), T(pts[:, 3:].copy())
+    _, idx = torch.ops.ri.knn_one(xyz, xyz, k)
+    fused = torch.ops.ri.ppf_gather(xyz, nrm, idx)                                    # [B,4,k,N]
+    gi = idx.reshape(B, 1, k * N).expand(-1, 3, -1).long()
+    p_xyz, p_nrm = torch.gather(xyz, 2, gi), torch.gather(nrm, 2, gi)
+    c_xyz = xyz[:, :, None, :].expand(-1, -1, k, -1).reshape(B, 3, k * N).contiguous()
+    c_nrm = nrm[:, :, None, :].expand(-1, -1, k, -1).reshape(B, 3, k * N).contiguous()
+    cols = ri.functional.ppf(c_xyz, p_xyz, c_nrm, p_nrm).reshape(B, 4, k, N)
+    assert torch.equal(fused, cols)
+    if ref_backend is not None:
+        r = ref_backend.spherical_ppf_forward(p_xyz.contiguous(), c_xyz, p_nrm.contiguous(), c_nrm).reshape(B, 4, k, N)
+        assert rel_err(A(fused), A(r)) <= TOL
+        assert torch.equal(fused, r)
+    # neighbour 0 is the point itself: direction undefined -> angles pi/2, ||d|| clamps to 1e-20
+    assert float((fused[:, 3, 0] - 1e-20).abs().max()) < 1e-26
+    assert float((fused[:, 0, 0] - np.pi / 2).abs().max()) < 1e-6
+
+
+# ================================================================================================ voxelize
+@pytest.mark.parametrize("r", [4, 8, 16, 32])
+def test_sph_voxelize_golden(ri, golden_dir, r):
+    g = load_golden(golden_dir, "spherical.npz")
+    out, ind, cnt = torch.ops.ri.sph_voxelize(T(g[f"r{r}_feat"]), T(g[f"r{r}_coords"]), r)
+    assert np.array_equal(A(ind), g[f"r{r}_ind"])
+    assert np.array_equal(A(cnt), g[f"r{r}_cnt"])
+    assert scaled_err(A(out), g[f"r{r}_out"]) <= TOL
+    gx = torch.ops.ri.voxelize_backward(T(g[f"r{r}_gy"]), ind, cnt)
+    assert rel_err(A(gx), g[f"r{r}_gx"]) <= TOL
+    o, di, dw = torch.ops.ri.sph_trilinear_devox(T(g[f"r{r}_coords"]), T(g[f"r{r}_grid"]), ind, r)
+    assert np.array_equal(A(di), g[f"r{r}_dinds"])
+    assert np.array_equal(A(dw), g[f"r{r}_dwgts"])
+    assert scaled_err(A(o), g[f"r{r}_douts"]) <= TOL
+    dgx = torch.ops.ri.devox_backward(T(g[f"r{r}_dgy"]), di, dw, r, True)
+    assert scaled_err(A(dgx), g[f"r{r}_dgx"]) <= TOL
+
+
+@pytest.mark.parametrize("r", [4, 8, 16])
+def test_cube_voxelize_golden(ri, golden_dir, r):
+    g = load_golden(golden_dir, "cube.npz")
+    out, ind, cnt = torch.ops.ri.cube_voxelize(T(g[f"r{r}_feat"]), T(g[f"r{r}_vox"]), r)
+    assert np.array_equal(A(ind), g[f"r{r}_ind"]) and np.array_equal(A(cnt), g[f"r{r}_cnt"])
+    assert scaled_err(A(out), g[f"r{r}_out"]) <= TOL
+    gx = torch.ops.ri.voxelize_backward(T(g[f"r{r}_gy"]), ind, cnt)
+    assert rel_err(A(gx), g[f"r{r}_gx"]) <= TOL
+    o, di, dw = torch.ops.ri.trilinear_devox(T(g[f"r{r}_norm_coords"]), T(g[f"r{r}_grid"]), r)
+    assert np.array_equal(A(di), g[f"r{r}_dinds"]) and np.array_equal(A(dw), g[f"r{r}_dwgts"])
+    assert np.array_equal(A(o), g[f"r{r}_douts"])
+    dgx = torch.ops.ri.devox_backward(T(g[f"r{r}_dgy"]), di, dw, r, False)
+    assert scaled_err(A(dgx), g[f"r{r}_dgx"]) <= TOL
+
+
+@pytest.mark.parametrize("B,N,C,r", [(32, 1024, 67, 32), (5, 1000, 9, 16), (3, 4096, 4, 64), (2, 777, 3, 8),
+                                      (2, 6000, 3, 32), (2, 500, 3, 5)])
+def test_sph_voxelize_vs_reference(ri, ref_backend, oracle, B, N, C, r):
+    """Live against the reference kernels at full and odd sizes.  (N=6000 and r=5 take the atomic fallback path.)"""
+    pts = clouds(B, N, 11 + r)
+    nc = sph_norm(T(pts[:, :3].copy()))
+    feat = torch.randn(B, C, N, device="cuda")
+    out, ind, cnt = torch.ops.ri.sph_voxelize(feat, nc, r)
+    assert int(cnt.sum()) == int((ind >= 0).sum())
+    if ref_backend is not None:
+        rout, rind, rcnt = ref_backend.spherical_avg_voxelize_forward(feat, nc, r)
+        assert torch.equal(ind, rind), "voxel indices differ from the reference kernel"
+        assert torch.equal(cnt, rcnt)
+        assert scaled_err(A(out), A(rout)) <= TOL
+    oi, oc = oracle.sph_grid_stats(A(nc), r)
+    mism = int((oi != A(ind)).sum())
+    assert mism <= max(2, B * N // 2000), "CPU oracle (libm acosf/atanf) disagrees on %d points" % mism
+    if mism == 0:
+        omean = oracle.scatter_mean(A(feat), oi, oc, r)
+        assert scaled_err(A(out), omean) <= TOL
+        if N <= 4096 and r % 2 == 0:
+            assert np.array_equal(A(out), omean)      # tiled path sums in point order, exactly like the oracle
+
+
+@pytest.mark.parametrize("B,N,C,r", [(32, 1024, 71, 32), (4, 900, 6, 16), (2, 5000, 3, 32)])
+def test_cube_pipeline_vs_reference(ri, ref_backend, oracle, B, N, C, r):
+    pts = clouds(B, N, 21)
+    vox_mod = ri.modules.Voxelization(r, normalize=False)
+    feat = torch.randn(B, C, N, device="cuda")
+    out, ind, nc = vox_mod(feat, T(pts[:, :3].copy()))
+    vc = torch.round(nc).to(torch.int32).contiguous()
+    if ref_backend is not None:
+        rout, rind, rcnt = ref_backend.avg_voxelize_forward(feat, vc, r)
+        assert torch.equal(ind, rind.view(B, N))
+        assert scaled_err(A(out.reshape(B, C, -1)), A(rout)) <= TOL
+        grid = torch.randn(B, 8, r, r, r, device="cuda")
+        d = ri.functional.trilinear_devoxelize(grid, nc, r, True)
+        ro, ri_, rw = ref_backend.trilinear_devoxelize_forward(r, True, nc.contiguous(), grid.view(B, 8, -1))
+        assert torch.equal(d, ro)
+    oout, oind, ocnt = oracle.avg_voxelize(A(feat), A(vc), r)
+    assert np.array_equal(A(ind), oind)
+    assert scaled_err(A(out.reshape(B, C, -1)), oout) <= TOL
+
+
+def test_sph_devox_and_edge_vs_reference(ri, ref_backend, oracle):
+    B, N, C, r = 8, 1024, 64, 32
+    pts = clouds(B, N, 31)
+    nc = sph_norm(T(pts[:, :3].copy()))
+    feat = torch.randn(B, C, N, device="cuda")
+    avg, ind, cnt = torch.ops.ri.sph_voxelize(feat, nc, r)
+    grid = torch.randn(B, C, r ** 3, device="cuda")
+    o, di, dw = torch.ops.ri.sph_trilinear_devox(nc, grid, ind, r)
+    if ref_backend is not None:
+        ro, rdi, rdw = ref_backend.spherical_trilinear_devoxelize_forward(r, True, nc, grid, ind)
+        assert torch.equal(di, rdi) and torch.equal(dw, rdw)
+        assert torch.equal(o, ro)
+    oo, odi, odw = oracle.spherical_trilinear_devoxelize(A(nc), A(grid), A(ind), r)
+    assert (odi != A(di)).mean() < 1e-3
+    # edge features: reference PVConv block, restated with torch ops (pvconv.py:68-90)
+    mask = ind == -1
+    it = ind.clone(); it[mask] = 0
+    centre = avg.gather(2, it.unsqueeze(1).expand(-1, C, -1).long())
+    rel = feat - centre
+    rel[mask.unsqueeze(1).expand(-1, C, -1)] = 0
+    want = torch.cat((rel, feat), 1)
+    got = torch.ops.ri.voxel_edge_gather(avg, feat, ind)
+    assert torch.equal(got, want)
+    assert np.array_equal(A(got), oracle.voxel_edge_gather(A(avg), A(feat), A(ind)))
+
+
+# ================================================================================================ modules / engine
+def test_pvconv_forward_backward(ri):
+    torch.manual_seed(0)
+    B, N, C = 2, 512, 16
+    pts = T(clouds(B, N, 41)[:, :3].copy())
+    for shape in ("spherical", "cube"):
+        conv = ri.modules.PVConv(C, 32, 'dgcnn_kernel', shape, 3, 16, with_coeff=True, with_se=True, normalize=False).cuda()
+        feat = torch.randn(B, C, N, device="cuda", requires_grad=True)
+        out, c = conv((feat, pts))
+        assert out.shape == (B, 32, N) and torch.isfinite(out).all()
+        out.square().mean().backward()
+        assert feat.grad is not None and torch.isfinite(feat.grad).all() and float(feat.grad.abs().sum()) > 0
+        keys = set(conv.state_dict().keys())
+        assert "coefficient" in keys and "voxel_layers.0.weight" in keys and "point_layers.layers.0.weight" in keys
+
+
+def test_frontend_engine_matches_ops(ri):
+    B, N, C, k, r = 8, 1024, 19, 20, 32
+    pts = clouds(B, N, 51); feats = ri.synth.make_features(B, C, N, 51)
+    for shape in ("spherical", "cube"):
+        fe = ri.FrontEnd(B, N, C, k=k, r=r, voxel_shape=shape)
+        res = fe(pts, feats)
+        res = {kk: v.clone() for kk, v in res.items()}
+        xyz, nrm = T(pts[:, :3].copy()), T(pts[:, 3:].copy())
+        _, idx = torch.ops.ri.knn_one(xyz, xyz, k)
+        assert torch.equal(torch.ops.ri.ppf_gather(xyz, nrm, idx).cpu(), res["ppf"])
+        f = T(feats)
+        if shape == "spherical":
+            avg, ind, nc = ri.modules.Spherical_Voxelization(r)(f, xyz)
+            dv = ri.functional.spherical_trilinear_devoxelize(avg, nc, ind, r)
+        else:
+            avg, ind, nc = ri.modules.Voxelization(r, normalize=False)(f, xyz)
+            dv = ri.functional.trilinear_devoxelize(avg, nc, r)
+        assert torch.equal(dv.cpu(), res["devox"])
+        assert torch.equal(ri.functional.voxel_edge_features(avg, f, ind).cpu(), res["edge"])
+        again = fe(pts, feats)                           # graph replay is deterministic
+        assert all(torch.equal(again[kk], res[kk]) for kk in res)
+
+
+def test_error_behaviour(ri):
+    x = torch.randn(2, 3, 64)
+    with pytest.raises(RuntimeError):
+        torch.ops.ri.knn(x, x, 4)                        # CPU tensor -> RuntimeError, like CHECK_CUDA
+    xc = torch.randn(2, 64, 3, device="cuda").transpose(1, 2)
+    with pytest.raises(RuntimeError):
+        torch.ops.ri.knn(xc, xc, 4)                      # non-contiguous, like CHECK_CONTIGUOUS
+    with pytest.raises(RuntimeError):
+        torch.ops.ri.cube_voxelize(torch.randn(1, 2, 8, device="cuda"), torch.zeros(1, 3, 8, device="cuda"), 4)  # float coords
