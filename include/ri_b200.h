@@ -64,6 +64,18 @@ int ri_ppf_f32(const float* coords, const float* center, const float* normals, c
 int ri_ppf_gather_f32(const float* xyz, const float* normals, const int* idx, int B, int N, int k,
                       float* out, void* stream);
 
+/* ---- coordinate prologue of the voxelization modules -----------------------------------------------------
+ * Voxelization.forward (PVCNN/modules/voxelization.py:16-35) / Spherical_Voxelization.forward
+ * (PVCNN/modules/spherical_vox.py:14-23) after the per-cloud mean: centre, scale, clamp/round or divide by the
+ * largest radius, in one kernel.  points [B,pstride,N] (pstride 3 = xyz, 6 = xyz|normal), mean [B,3] (the caller's
+ * `coords.mean(2)`: its summation order defines the bits).  shape: 0 cube normalize=False, 1 cube normalize=True,
+ * 2 spherical.  Outputs: norm_coords [B,3,N] fp32 (always), vox_coords [B,3,N] i32 (shape 0/1), and optionally the
+ * de-interleaved xyz / normals planes [B,3,N] (null to skip).  norm_mode selects the association of the 3-term
+ * radius sum (1 = (x*x + y*y) + z*z without contraction, the one matching torch norm). */
+int ri_vox_prologue_f32(const float* points, int pstride, const float* mean, int B, int N, int r,
+                        int shape, float eps, int norm_mode,
+                        float* xyz, float* normals, float* norm_coords, int* vox_coords, void* stream);
+
 /* ---- voxelization ---------------------------------------------------------------------------------------
  * spherical_avg_voxelize_forward (spherical_voxelization/spherical_vox.cpp:17-46) and avg_voxelize_forward
  * (voxelization/vox.cpp:17-43).  feat [B,C,N]; coords [B,3,N] (fp32 normalised Cartesian for the spherical
@@ -75,6 +87,17 @@ int ri_sph_voxelize_f32(const float* feat, const float* coords, int B, int C, in
                         float* out, int* ind, int* cnt, void* workspace, size_t workspace_bytes, void* stream);
 int ri_cube_voxelize_f32(const float* feat, const int* coords, int B, int C, int N, int r,
                          float* out, int* ind, int* cnt, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused voxelize + DGCNN edge features: same as above and additionally edge [B,2C,N] =
+ * cat(feat - out[:, :, ind] (0 where ind == -1), feat), i.e. what ri_voxel_edge_gather_f32 would produce from `out`,
+ * emitted in the same pass (the voxelizer already holds each point's cell mean; the dense grid is not re-read).
+ * Replaces voxelize + PVCNN/modules/pvconv.py:68-90. */
+int ri_sph_voxelize_edge_f32(const float* feat, const float* coords, int B, int C, int N, int r,
+                             float* out, int* ind, int* cnt, float* edge,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int ri_cube_voxelize_edge_f32(const float* feat, const int* coords, int B, int C, int N, int r,
+                              float* out, int* ind, int* cnt, float* edge,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* avg_voxelize_backward == spherical_avg_voxelize_backward (vox.cpp:54-78, vox.cu:87-111):
  * grad_x [B,C,N] = grad_y[b,c,ind] / cnt (0 for undefined points); grad_x fully overwritten. */

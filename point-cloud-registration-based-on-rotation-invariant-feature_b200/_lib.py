@@ -18,9 +18,12 @@ SIGNATURES = {
     "ri_knn_backward_f32": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ri_ppf_f32": (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
     "ri_ppf_gather_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "ri_vox_prologue_f32": (_I, [_P, _I, _P, _I, _I, _I, _I, ctypes.c_float, _I, _P, _P, _P, _P, _P]),
     "ri_voxelize_workspace_bytes": (_Z, [_I, _I, _I]),
     "ri_sph_voxelize_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
     "ri_cube_voxelize_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
+    "ri_sph_voxelize_edge_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    "ri_cube_voxelize_edge_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "ri_voxelize_backward_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "ri_trilinear_devox_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "ri_sph_trilinear_devox_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),

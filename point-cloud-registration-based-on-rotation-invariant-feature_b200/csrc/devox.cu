@@ -42,7 +42,9 @@ __global__ void __launch_bounds__(kDevoxThreads)
 devox_kernel(const float* __restrict__ coords, const float* __restrict__ feat, const int* __restrict__ g_inds,
              int C, int N, int r, float* __restrict__ outs, int* __restrict__ inds, float* __restrict__ wgts)
 {
-    const int b = blockIdx.z;
+    // Clouds are walked in DESCENDING order: when the grid was produced just before by a kernel that wrote clouds
+    // in ascending order (the voxelizer, a Conv3d), the highest-numbered clouds are the ones still resident in L2.
+    const int b = (int)gridDim.z - 1 - (int)blockIdx.z;
     const int i = blockIdx.x * kDevoxThreads + threadIdx.x;
     if (i >= N) return;
     const int r2 = r * r;

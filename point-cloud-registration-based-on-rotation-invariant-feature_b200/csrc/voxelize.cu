@@ -28,6 +28,10 @@
 //   Fallback (N > 4096 points per cloud, r^3 not a multiple of 4, or misaligned pointers): memset + integer
 //   atomics for counts + float atomics for the means over a (point tile, channel group, cloud) grid.
 #include "ri_common.cuh"
+#include <stdlib.h>
+
+extern "C" int ri_voxel_edge_gather_f32(const float* avg, const float* feat, const int* inds, int B, int C, int N, int s,
+                                        float* out, void* stream);
 
 namespace {
 
@@ -36,6 +40,8 @@ constexpr int kSmallCloudMax = 4096;     // K1 sorts a whole cloud inside one CT
 constexpr int kTileCells = 8192;         // 32 KB of fp32 per tile
 constexpr int kRing = 3;                 // tiles in flight per CTA
 constexpr int kFillThreads = 256;
+constexpr int kSegCache = 4;             // occupied cells per thread whose table entries live in registers
+constexpr unsigned kNoCell = 0xffffffffu;
 
 struct VoxWs {                            // per-cloud int32 workspace layout
     int stride, off_pid, off_cell, off_start, off_tile, off_meta;
@@ -82,7 +88,10 @@ vox_prepare_kernel(const void* __restrict__ coords_v, int N, int P, int r, int s
                 cell = X[i] * r * r + X[i + N] * r + X[i + 2 * (size_t)N];          // vox.cu:31
             }
             ind[(size_t)b * N + i] = cell;
-            if (cell >= 0 && cell < s) key = ((unsigned long long)(unsigned)cell << 32) | (unsigned)i;
+            // points outside the grid sort behind every occupied cell but keep their id (the fused edge
+            // output still has to be written for them)
+            const unsigned hi = (cell >= 0 && cell < s) ? (unsigned)cell : kNoCell;
+            key = ((unsigned long long)hi << 32) | (unsigned)i;
         }
         skeys[i] = key;
     }
@@ -110,7 +119,7 @@ vox_prepare_kernel(const void* __restrict__ coords_v, int N, int P, int r, int s
         const int u = u0 + e;
         if (u < P) {
             const unsigned long long key = skeys[u];
-            if (key != ~0ull) {
+            if ((unsigned)(key >> 32) != kNoCell) {
                 ++valid;
                 if (u == 0 || (unsigned)(skeys[u - 1] >> 32) != (unsigned)(key >> 32)) ++heads;
             }
@@ -152,8 +161,8 @@ vox_prepare_kernel(const void* __restrict__ coords_v, int N, int P, int r, int s
         const int u = u0 + e;
         if (u < P) {
             const unsigned long long key = skeys[u];
-            if (key != ~0ull) {
-                W[L.off_pid + u] = (int)(unsigned)(key & 0xffffffffu);
+            if (u < N) W[L.off_pid + u] = (int)(unsigned)(key & 0xffffffffu);
+            if ((unsigned)(key >> 32) != kNoCell) {
                 const unsigned cell = (unsigned)(key >> 32);
                 if (u == 0 || (unsigned)(skeys[u - 1] >> 32) != cell) {
                     W[L.off_cell + seg] = (int)cell;
@@ -179,10 +188,36 @@ vox_prepare_kernel(const void* __restrict__ coords_v, int N, int P, int r, int s
 }
 
 // ------------------------------------------------------------------------------------------------ K2
+// One occupied cell ("segment" of the cell-sorted point list) of the current tile, as cached by its thread.
+struct SegRegs { int off, st, cnt; };
+
+// Mean of channel plane p over one segment (ascending point order), or the count itself for plane C.
+// When `edge` is given also emits the DGCNN edge features of the segment's points:
+//   edge[b, p, i] = feat - mean,  edge[b, C+p, i] = feat      (pvconv.py:68-90; undefined points: see below)
+__device__ __forceinline__ float seg_value(const SegRegs sg, int p, int C, int N, const float* __restrict__ Fp,
+                                           const int* __restrict__ pid, float* __restrict__ edge_rel,
+                                           float* __restrict__ edge_cpy)
+{
+    if (p >= C) return __int_as_float(sg.cnt);
+    const float inv = __fdiv_rn(1.0f, (float)sg.cnt);                               // vox.cu:66
+    float acc = 0.f;
+    for (int u = sg.st; u < sg.st + sg.cnt; ++u)
+        acc = __fadd_rn(acc, __fmul_rn(__ldg(Fp + __ldg(pid + u)), inv));          // vox.cu:68-70, point order
+    if (edge_rel != nullptr) {
+        for (int u = sg.st; u < sg.st + sg.cnt; ++u) {
+            const int i = __ldg(pid + u);
+            const float f = __ldg(Fp + i);
+            edge_rel[i] = __fsub_rn(f, acc);
+            edge_cpy[i] = f;
+        }
+    }
+    return acc;
+}
+
 __global__ void __launch_bounds__(kFillThreads, 2)
 vox_fill_kernel(const float* __restrict__ feat, const int* __restrict__ ws, int B, int C, int N, int s,
                 int tile_cells, int ntiles, int planes_per_item, int ngroups,
-                float* __restrict__ out, int* __restrict__ cnt)
+                float* __restrict__ out, int* __restrict__ cnt, float* __restrict__ edge)
 {
     extern __shared__ __align__(128) float sring[];        // kRing tiles of tile_cells floats
     const int tid = threadIdx.x;
@@ -191,11 +226,32 @@ vox_fill_kernel(const float* __restrict__ feat, const int* __restrict__ ws, int 
 
     for (int i = tid; i < kRing * tile_cells / 4; i += kFillThreads)
         reinterpret_cast<float4*>(sring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
 
     const long long total = (long long)B * ntiles * ngroups;
     int slot = 0;
-    int prev_sA = 0, prev_sB = 0, prev_lo = 0;
-    const int* prevW = nullptr;
+    // The ring slots are never re-zeroed wholesale.  Between two bulk copies out of a slot only the occupied cells
+    // of the tile are rewritten; when the CTA moves on to another (cloud, tile) the cells of the PREVIOUS item are
+    // cleared lazily, slot by slot, right before each slot's first reuse — so the copies still in flight are never
+    // waited for (no pipeline drain at an item switch).
+    SegRegs seg[kSegCache];                                 // this item's cells owned by this thread
+    int old_off[kSegCache];                                 // previous item's cells (offset, or -1)
+#pragma unroll
+    for (int q = 0; q < kSegCache; ++q) { seg[q].off = 0; seg[q].st = 0; seg[q].cnt = 0; old_off[q] = -1; }
+    int extra_lo = 0, extra_hi = 0, cur_cell_lo = 0;        // cells beyond the register cache (rare), current item
+    int old_extra_lo = 0, old_extra_hi = 0, old_cell_lo = 0;
+    const int* curW = nullptr;
+    const int* oldW = nullptr;
+    int stale = 0;                                          // ring slots that still carry the previous item's cells
+    int prev_planes = kRing;
+
+    auto unpatch_slot = [&](float* tile) {
+#pragma unroll
+        for (int q = 0; q < kSegCache; ++q)
+            if (old_off[q] >= 0) tile[old_off[q]] = 0.f;
+        for (int sg = old_extra_lo + tid; sg < old_extra_hi; sg += kFillThreads)
+            tile[__ldg(oldW + L.off_cell + sg) - old_cell_lo] = 0.f;
+    };
 
     for (long long item = blockIdx.x; item < total; item += gridDim.x) {
         // item -> (cloud, tile, plane group); groups of one (cloud,tile) are adjacent so neighbouring CTAs
@@ -205,43 +261,97 @@ vox_fill_kernel(const float* __restrict__ feat, const int* __restrict__ ws, int 
         const int t = (int)(bt % ntiles);
         const int b = (int)(bt / ntiles);
         const int* W = ws + (size_t)b * L.stride;
+        const int* pid = W + L.off_pid;
         const int cell_lo = t * tile_cells;
         const int ncell = min(tile_cells, s - cell_lo);
         const int sA = __ldg(W + L.off_tile + t), sB = __ldg(W + L.off_tile + t + 1);
         const int p0 = g * planes_per_item, p1 = min(planes, p0 + planes_per_item);
 
-        // un-patch the ring: the previous item's occupied cells are the only non-zero words in it
-        if (tid == 0) ri_bulk_wait_read<0>();
-        __syncthreads();
-        if (prevW != nullptr) {
-            for (int sg = prev_sA + tid; sg < prev_sB; sg += kFillThreads) {
-                const int off = __ldg(prevW + L.off_cell + sg) - prev_lo;
+        if (curW != nullptr) {
+            if (stale > 0 || prev_planes < kRing) {
+                // the previous item did not cycle through the whole ring: clean everything the slow way
+                if (tid == 0) ri_bulk_wait_read<0>();
+                __syncthreads();
+                for (int k2 = 0; k2 < kRing; ++k2) {
+                    float* tile = sring + k2 * tile_cells;
+                    if (stale > 0) unpatch_slot(tile);
 #pragma unroll
-                for (int q = 0; q < kRing; ++q) sring[q * tile_cells + off] = 0.f;
+                    for (int q = 0; q < kSegCache; ++q)
+                        if (seg[q].cnt > 0) tile[seg[q].off] = 0.f;
+                    for (int sg = extra_lo + tid; sg < extra_hi; sg += kFillThreads)
+                        tile[__ldg(curW + L.off_cell + sg) - cur_cell_lo] = 0.f;
+                }
+                __syncthreads();
+                stale = 0;
+#pragma unroll
+                for (int q = 0; q < kSegCache; ++q) old_off[q] = -1;
+                old_extra_lo = old_extra_hi = 0;
+            } else {
+#pragma unroll
+                for (int q = 0; q < kSegCache; ++q) old_off[q] = seg[q].cnt > 0 ? seg[q].off : -1;
+                old_extra_lo = extra_lo; old_extra_hi = extra_hi; old_cell_lo = cur_cell_lo; oldW = curW;
+                stale = kRing;
             }
         }
-        prevW = W; prev_sA = sA; prev_sB = sB; prev_lo = cell_lo;
-        // (the __syncthreads at the top of the plane loop orders these stores before the patching)
+        // this item's table entries -> registers
+#pragma unroll
+        for (int q = 0; q < kSegCache; ++q) {
+            const int sg = sA + tid + q * kFillThreads;
+            seg[q].cnt = 0;
+            if (sg < sB) {
+                seg[q].off = __ldg(W + L.off_cell + sg) - cell_lo;
+                seg[q].st = __ldg(W + L.off_start + sg);
+                seg[q].cnt = __ldg(W + L.off_start + sg + 1) - seg[q].st;
+            }
+        }
+        extra_lo = min(sB, sA + kSegCache * kFillThreads); extra_hi = sB; cur_cell_lo = cell_lo; curW = W;
+        prev_planes = p1 - p0;
 
+        // undefined points of this cloud (ind == -1): edge rows are (0, feat); done once per plane group
+        if (edge != nullptr && t == 0) {
+            const int nvalid = __ldg(W + L.off_meta + 1);
+            for (int u = nvalid + tid; u < N; u += kFillThreads) {
+                const int i = __ldg(pid + u);
+                for (int p = p0; p < min(p1, C); ++p) {
+                    edge[((size_t)b * 2 * C + p) * N + i] = 0.f;
+                    edge[((size_t)b * 2 * C + C + p) * N + i] = __ldg(feat + ((size_t)b * C + p) * N + i);
+                }
+            }
+        }
+
+        float val[kSegCache];
+        auto compute = [&](int p) {
+            const float* Fp = feat + ((size_t)b * C + (p < C ? p : 0)) * N;
+            float* er = (edge != nullptr && p < C) ? edge + ((size_t)b * 2 * C + p) * N : nullptr;
+            float* ec = (edge != nullptr && p < C) ? edge + ((size_t)b * 2 * C + C + p) * N : nullptr;
+#pragma unroll
+            for (int q = 0; q < kSegCache; ++q)
+                if (seg[q].cnt > 0) val[q] = seg_value(seg[q], p, C, N, Fp, pid, er, ec);
+        };
+        compute(p0);
         for (int p = p0; p < p1; ++p) {
             float* tile = sring + slot * tile_cells;
             if (tid == 0) ri_bulk_wait_read<kRing - 1>();  // the copy that last used this slot has left smem
             __syncthreads();
-            const float* F = feat + ((size_t)b * C + (p < C ? p : 0)) * N;
-            for (int sg = sA + tid; sg < sB; sg += kFillThreads) {
-                const int cell = __ldg(W + L.off_cell + sg);
-                const int st = __ldg(W + L.off_start + sg), en = __ldg(W + L.off_start + sg + 1);
-                float val;
-                if (p < C) {
-                    const float inv = __fdiv_rn(1.0f, (float)(en - st));               // vox.cu:66
-                    float acc = 0.f;
-                    for (int u = st; u < en; ++u)
-                        acc = __fadd_rn(acc, __fmul_rn(__ldg(F + __ldg(W + L.off_pid + u)), inv));
-                    val = acc;
-                } else {
-                    val = __int_as_float(en - st);
+            if (stale > 0) {                                // first reuse of this slot since the item switch
+                unpatch_slot(tile);
+                --stale;
+                __syncthreads();                            // an old cell may coincide with a new one of another thread
+            }
+#pragma unroll
+            for (int q = 0; q < kSegCache; ++q)
+                if (seg[q].cnt > 0) tile[seg[q].off] = val[q];
+            if (extra_lo < extra_hi) {                      // cells beyond the register cache: direct path
+                const float* Fp = feat + ((size_t)b * C + (p < C ? p : 0)) * N;
+                float* er = (edge != nullptr && p < C) ? edge + ((size_t)b * 2 * C + p) * N : nullptr;
+                float* ec = (edge != nullptr && p < C) ? edge + ((size_t)b * 2 * C + C + p) * N : nullptr;
+                for (int sg = extra_lo + tid; sg < extra_hi; sg += kFillThreads) {
+                    SegRegs x;
+                    x.off = __ldg(W + L.off_cell + sg) - cell_lo;
+                    x.st = __ldg(W + L.off_start + sg);
+                    x.cnt = __ldg(W + L.off_start + sg + 1) - x.st;
+                    tile[x.off] = seg_value(x, p, C, N, Fp, pid, er, ec);
                 }
-                tile[cell - cell_lo] = val;
             }
             ri_fence_proxy_async_smem();
             __syncthreads();
@@ -252,6 +362,7 @@ vox_fill_kernel(const float* __restrict__ feat, const int* __restrict__ ws, int 
                 ri_bulk_commit();
             }
             slot = (slot + 1 == kRing) ? 0 : slot + 1;
+            if (p + 1 < p1) compute(p + 1);                 // gathers of the next plane overlap this plane's store
         }
     }
     if (tid == 0) ri_bulk_wait<0>();
@@ -312,9 +423,15 @@ VoxPlan vox_plan(int N, int r, const void* out, const void* cnt)
     return p;
 }
 
+int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 template <bool SPH>
 int voxelize_impl(const float* feat, const void* coords, int B, int C, int N, int r,
-                  float* out, int* ind, int* cnt, void* workspace, size_t ws_bytes, cudaStream_t st)
+                  float* out, int* ind, int* cnt, float* edge, void* workspace, size_t ws_bytes, cudaStream_t st)
 {
     if (B < 0 || C < 0 || N < 0 || r <= 0 || r > 1024) return RI_ERR_BAD_ARG;
     const long long s_ll = (long long)r * r * r;
@@ -342,16 +459,18 @@ int voxelize_impl(const float* feat, const void* coords, int B, int C, int N, in
         const int planes = C + 1;
         const long long bt = (long long)B * plan.ntiles;
         long long grid = 2LL * sms;
-        long long want_groups = (8 * grid + bt - 1) / bt;          // ~8 items per CTA for balance
+        static const int items_per_cta = env_int("RI_VOX_ITEMS_PER_CTA", 4);
+        static const int min_planes = env_int("RI_VOX_MIN_PLANES", 6);
+        long long want_groups = ((long long)items_per_cta * grid + bt - 1) / bt;   // a few items per CTA for balance
         if (want_groups < 1) want_groups = 1;
         if (want_groups > planes) want_groups = planes;
         int ppi = (int)((planes + want_groups - 1) / want_groups);
-        if (ppi < 2 && planes >= 2) ppi = 2;
+        if (ppi < min_planes) ppi = min_planes < planes ? min_planes : planes;
         const int ngroups = (planes + ppi - 1) / ppi;
         const long long total = bt * ngroups;
         if (grid > total) grid = total;
         vox_fill_kernel<<<(unsigned)grid, kFillThreads, smem2, st>>>(feat, ws, B, C, N, s, plan.tile_cells, plan.ntiles,
-                                                                     ppi, ngroups, out, cnt);
+                                                                     ppi, ngroups, out, cnt, edge);
         RI_LAUNCH_CHECK();
         return RI_OK;
     }
@@ -369,6 +488,7 @@ int voxelize_impl(const float* feat, const void* coords, int B, int C, int N, in
         dim3 g2((N + 255) / 256, (C + kScatterChans - 1) / kScatterChans, B);
         vox_scatter_atomic_kernel<<<g2, 256, 0, st>>>(feat, ind, cnt, C, N, s, out);
         RI_LAUNCH_CHECK();
+        if (edge != nullptr) return ri_voxel_edge_gather_f32(out, feat, ind, B, C, N, s, edge, (void*)st);
     }
     return RI_OK;
 }
@@ -387,11 +507,29 @@ extern "C" size_t ri_voxelize_workspace_bytes(int B, int N, int r)
 extern "C" int ri_sph_voxelize_f32(const float* feat, const float* coords, int B, int C, int N, int r,
                                    float* out, int* ind, int* cnt, void* workspace, size_t ws_bytes, void* stream)
 {
-    return voxelize_impl<true>(feat, coords, B, C, N, r, out, ind, cnt, workspace, ws_bytes, (cudaStream_t)stream);
+    return voxelize_impl<true>(feat, coords, B, C, N, r, out, ind, cnt, nullptr, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int ri_cube_voxelize_f32(const float* feat, const int* coords, int B, int C, int N, int r,
                                     float* out, int* ind, int* cnt, void* workspace, size_t ws_bytes, void* stream)
 {
-    return voxelize_impl<false>(feat, coords, B, C, N, r, out, ind, cnt, workspace, ws_bytes, (cudaStream_t)stream);
+    return voxelize_impl<false>(feat, coords, B, C, N, r, out, ind, cnt, nullptr, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+// Fused forms: voxelize AND emit the DGCNN edge features edge [B,2C,N] of the same points in the same pass
+// (the voxelizer already holds every point's cell mean), so PVConv's gather never re-reads the dense grid.
+extern "C" int ri_sph_voxelize_edge_f32(const float* feat, const float* coords, int B, int C, int N, int r,
+                                        float* out, int* ind, int* cnt, float* edge,
+                                        void* workspace, size_t ws_bytes, void* stream)
+{
+    if (edge == nullptr) return RI_ERR_BAD_ARG;
+    return voxelize_impl<true>(feat, coords, B, C, N, r, out, ind, cnt, edge, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int ri_cube_voxelize_edge_f32(const float* feat, const int* coords, int B, int C, int N, int r,
+                                         float* out, int* ind, int* cnt, float* edge,
+                                         void* workspace, size_t ws_bytes, void* stream)
+{
+    if (edge == nullptr) return RI_ERR_BAD_ARG;
+    return voxelize_impl<false>(feat, coords, B, C, N, r, out, ind, cnt, edge, workspace, ws_bytes, (cudaStream_t)stream);
 }

@@ -4,9 +4,10 @@ One "step" takes a batch of clouds (xyz | normal, [B,6,N]) and their per-point i
 produces everything the dense layers of a PVConv block consume (SURVEY.md §3 call stack A, §8 rows a1-a10):
 
     branch A (ALU bound)      k-NN self query  ->  fused neighbour gather + PPF          -> ppf   [B,4,k,N]
-    branch B (HBM bound)      coordinate prologue (torch, defines the bits) -> voxelize  -> grid  [B,C,r,r,r], ind, cnt
+    branch B (HBM bound)      coordinate prologue (torch mean + one kernel) -> voxelize        -> grid  [B,C,r,r,r], ind, cnt
                               -> trilinear devoxelize of the grid                        -> devox [B,C,N]
-                              -> DGCNN voxel-neighbour edge features                     -> edge  [B,2C,N]
+                              (the voxelizer emits the DGCNN voxel-neighbour edge features -> edge [B,2C,N]
+                               in the same pass: it already holds every point's cell mean)
 
 The two branches are independent, so they run on two streams inside one captured CUDA graph: the brute-force
 k-NN (register/ALU bound) overlaps the dense grid write (HBM bound).  All buffers are allocated once; the kernels
@@ -25,7 +26,8 @@ _check = _lib.check
 
 
 class FrontEnd:
-    KERNELS_PER_STEP = 6     # knn, ppf_gather, vox_prepare, vox_fill, devox, edge_gather (this package's own kernels)
+    KERNELS_PER_STEP = 6     # knn, ppf_gather, vox_prologue, vox_prepare, vox_fill (+fused edge features), devox
+    NORM_MODE = 1            # association of the 3-term radius sum that matches torch's norm kernel (see prologue.cu)
 
     def __init__(self, B, N, C, k=20, r=32, voxel_shape='spherical', normalize=False, eps=0.0,
                  device='cuda', use_graph=True, overlap=True):
@@ -56,6 +58,10 @@ class FrontEnd:
             self.devox_inds = torch.empty((B, 8, N), dtype=i32, device=dev)
             self.devox_wgts = torch.empty((B, 8, N), dtype=f32, device=dev)
             self.edge = torch.empty((B, 2 * C, N), dtype=f32, device=dev)
+            self.xyz = torch.empty((B, 3, N), dtype=f32, device=dev)
+            self.normals = torch.empty((B, 3, N), dtype=f32, device=dev)
+            self.norm_coords = torch.empty((B, 3, N), dtype=f32, device=dev)
+            self._vox_coords = torch.empty((B, 3, N), dtype=i32, device=dev)
             self._ws_bytes = _L.ri_voxelize_workspace_bytes(B, N, r)
             self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=dev)
             self._side = torch.cuda.Stream(device=dev)
@@ -66,7 +72,6 @@ class FrontEnd:
             self.h_devox = torch.empty((B, C, N), dtype=f32).pin_memory()
             self.h_edge = torch.empty((B, 2 * C, N), dtype=f32).pin_memory()
         self._graph = None
-        self.norm_coords = None
 
     # bytes moved per host-facing call
     @property
@@ -81,49 +86,44 @@ class FrontEnd:
     def _branch_a(self):
         st = torch.cuda.current_stream().cuda_stream
         B, N, k = self.B, self.N, self.k
-        xyz = self._xyz
-        _check(_L.ri_knn_f32(xyz.data_ptr(), xyz.data_ptr(), B, 3, N, N, k,
+        self.xyz.copy_(self.points[:, :3, :])
+        self.normals.copy_(self.points[:, 3:6, :])
+        _check(_L.ri_knn_f32(self.xyz.data_ptr(), self.xyz.data_ptr(), B, 3, N, N, k,
                              self.knn_dist.data_ptr(), self.knn_idx.data_ptr(), st), 'ri_knn')
-        _check(_L.ri_ppf_gather_f32(xyz.data_ptr(), self._nrm.data_ptr(), self.knn_idx.data_ptr(), B, N, k,
+        _check(_L.ri_ppf_gather_f32(self.xyz.data_ptr(), self.normals.data_ptr(), self.knn_idx.data_ptr(), B, N, k,
                                     self.ppf.data_ptr(), st), 'ri_ppf_gather')
 
     def _branch_b(self):
         st = torch.cuda.current_stream().cuda_stream
         B, N, C, r = self.B, self.N, self.C, self.r
-        coords = self._xyz
-        # coordinate prologue: torch ops, exactly the module shells (modules/voxelization.py), because these
-        # reductions define the bits the binning kernel must see.
-        nc = coords - coords.mean(2, keepdim=True)
-        if self.voxel_shape == 'spherical':
-            nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values + 1e-20)
-            self.norm_coords = nc
-            _check(_L.ri_sph_voxelize_f32(self.features.data_ptr(), nc.data_ptr(), B, C, N, r,
-                                          self.grid.data_ptr(), self.ind.data_ptr(), self.cnt.data_ptr(),
-                                          self._ws.data_ptr(), self._ws_bytes, st), 'ri_sph_voxelize')
+        # Coordinate prologue.  The per-cloud mean stays torch's own reduction (its summation order defines the bits
+        # the binning must see); everything after it is one kernel, bit-identical to the module shells
+        # (modules/voxelization.py) — asserted by tests/test_parity_gpu.py.
+        mean = self.points[:, :3, :].mean(2)
+        sph = self.voxel_shape == 'spherical'
+        shape = 2 if sph else (1 if self.normalize else 0)
+        _check(_L.ri_vox_prologue_f32(self.points.data_ptr(), 6, mean.data_ptr(), B, N, r, shape, float(self.eps),
+                                      self.NORM_MODE, None, None, self.norm_coords.data_ptr(),
+                                      self._vox_coords.data_ptr(), st), 'ri_vox_prologue')
+        nc = self.norm_coords
+        if sph:
+            _check(_L.ri_sph_voxelize_edge_f32(self.features.data_ptr(), nc.data_ptr(), B, C, N, r,
+                                               self.grid.data_ptr(), self.ind.data_ptr(), self.cnt.data_ptr(),
+                                               self.edge.data_ptr(), self._ws.data_ptr(), self._ws_bytes, st),
+                   'ri_sph_voxelize_edge')
             _check(_L.ri_sph_trilinear_devox_f32(nc.data_ptr(), self.grid.data_ptr(), self.ind.data_ptr(), B, C, N, r,
                                                  self.devox.data_ptr(), self.devox_inds.data_ptr(),
                                                  self.devox_wgts.data_ptr(), st), 'ri_sph_trilinear_devox')
         else:
-            if self.normalize:
-                nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + self.eps) + 0.5
-            else:
-                nc = (nc + 1) / 2.0
-            nc = torch.clamp(nc * r, 0, r - 1)
-            vox = torch.round(nc).to(torch.int32)
-            self.norm_coords = nc
-            self._vox_coords = vox
-            _check(_L.ri_cube_voxelize_f32(self.features.data_ptr(), vox.data_ptr(), B, C, N, r,
-                                           self.grid.data_ptr(), self.ind.data_ptr(), self.cnt.data_ptr(),
-                                           self._ws.data_ptr(), self._ws_bytes, st), 'ri_cube_voxelize')
+            _check(_L.ri_cube_voxelize_edge_f32(self.features.data_ptr(), self._vox_coords.data_ptr(), B, C, N, r,
+                                                self.grid.data_ptr(), self.ind.data_ptr(), self.cnt.data_ptr(),
+                                                self.edge.data_ptr(), self._ws.data_ptr(), self._ws_bytes, st),
+                   'ri_cube_voxelize_edge')
             _check(_L.ri_trilinear_devox_f32(nc.data_ptr(), self.grid.data_ptr(), B, C, N, r,
                                              self.devox.data_ptr(), self.devox_inds.data_ptr(),
                                              self.devox_wgts.data_ptr(), st), 'ri_trilinear_devox')
-        _check(_L.ri_voxel_edge_gather_f32(self.grid.data_ptr(), self.features.data_ptr(), self.ind.data_ptr(),
-                                           B, C, N, r ** 3, self.edge.data_ptr(), st), 'ri_voxel_edge_gather')
 
     def _step(self):
-        self._xyz = self.points[:, :3, :].contiguous()
-        self._nrm = self.points[:, 3:6, :].contiguous()
         if self.overlap:
             main = torch.cuda.current_stream()
             self._side.wait_stream(main)

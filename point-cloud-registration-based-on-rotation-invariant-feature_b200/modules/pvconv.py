@@ -2,8 +2,9 @@
 same state_dict keys: voxel_layers.*, point_layers.*, coefficient), running on the ri_b200 ops.
 
 Difference in mechanism only: the DGCNN voxel-neighbour grouping (pvconv.py:68-90: deepcopy + int64 index
-expansion + gather + boolean-mask scatter + cat + two `.sum() > 0` host synchronisations) is one custom op,
-`voxel_edge_features`."""
+expansion + gather + boolean-mask scatter + cat + two `.sum() > 0` host synchronisations) is emitted by the
+voxelizer itself in the same pass (`with_edge=True`), so the dense grid is never gathered from.
+`functional.voxel_edge_features` is the standalone form of the same computation."""
 import torch
 import torch.nn as nn
 
@@ -46,19 +47,21 @@ class PVConv(nn.Module):
 
     def forward(self, inputs):
         features, coords = inputs
+        dgcnn = self.point_kernel_formal == 'dgcnn_kernel'
+        edge = None
         if self.voxel_shape == 'cube':
-            avg_voxel_features, inds, voxel_coords = self.voxelization(features, coords)
+            avg_voxel_features, inds, voxel_coords, *edge = self.voxelization(features, coords, with_edge=dgcnn)
             voxel_features = self.voxel_layers(avg_voxel_features)
             voxel_features = F.trilinear_devoxelize(voxel_features, voxel_coords, self.resolution, self.training)
         elif self.voxel_shape == 'spherical':
-            avg_voxel_features, inds, voxel_coords = self.spherical_vox(features, coords)
+            avg_voxel_features, inds, voxel_coords, *edge = self.spherical_vox(features, coords, with_edge=dgcnn)
             voxel_features = self.voxel_layers(avg_voxel_features)
             voxel_features = F.spherical_trilinear_devoxelize(voxel_features, voxel_coords, inds, self.resolution,
                                                               self.training)
         else:
             raise ValueError('voxel_shape must be "cube" or "spherical"')
-        if self.point_kernel_formal == 'dgcnn_kernel':
-            point_features = self.point_layers(F.voxel_edge_features(avg_voxel_features, features, inds))
+        if dgcnn:
+            point_features = self.point_layers(edge[0])
         elif self.point_kernel_formal == 'pointnet_kernel':
             point_features = self.point_layers(features)
         else:

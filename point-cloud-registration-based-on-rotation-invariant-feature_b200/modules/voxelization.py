@@ -19,9 +19,10 @@ class Voxelization(nn.Module):
         self.normalize = normalize
         self.eps = eps
 
-    def forward(self, features, coords):
+    def forward(self, features, coords, with_edge=False):
         """features [B,C,N], coords [B,3,N] -> (voxel means [B,C,r,r,r], voxel index per point [B,N],
-        continuous grid coordinates [B,3,N] in [0, r-1] (what trilinear_devoxelize consumes))."""
+        continuous grid coordinates [B,3,N] in [0, r-1] (what trilinear_devoxelize consumes)).
+        with_edge=True (extension) appends the DGCNN edge features [B,2C,N] produced in the same pass."""
         coords = coords.detach()
         norm_coords = coords - coords.mean(2, keepdim=True)
         if self.normalize:
@@ -31,6 +32,9 @@ class Voxelization(nn.Module):
             norm_coords = (norm_coords + 1) / 2.0
         norm_coords = torch.clamp(norm_coords * self.r, 0, self.r - 1)
         vox_coords = torch.round(norm_coords).to(torch.int32)
+        if with_edge:
+            out, indices, edge = F.avg_voxelize_edge(features, vox_coords, self.r)
+            return out, indices.detach(), norm_coords, edge
         out, indices = F.avg_voxelize(features, vox_coords, self.r)
         return out, indices.detach(), norm_coords
 
@@ -43,12 +47,16 @@ class Spherical_Voxelization(nn.Module):
         super().__init__()
         self.r = int(resolution)
 
-    def forward(self, features, coords):
+    def forward(self, features, coords, with_edge=False):
         """features [B,C,N], coords [B,3,N] -> (means on the spherical grid [B,C,r,r,r], cell per point [B,N]
-        (-1 = undefined), centred coords scaled so the farthest point has radius ~1)."""
+        (-1 = undefined), centred coords scaled so the farthest point has radius ~1).
+        with_edge=True (extension) appends the DGCNN edge features [B,2C,N] produced in the same pass."""
         coords = coords.detach()
         norm_coords = coords - coords.mean(2, keepdim=True)
         norm_coords = norm_coords / (norm_coords.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values + 1e-20)
+        if with_edge:
+            out, inds, edge = F.spherical_avg_voxelize_edge(features, norm_coords, self.r)
+            return out, inds.detach(), norm_coords, edge
         out, inds = F.spherical_avg_voxelize(features, norm_coords, self.r)
         return out, inds.detach(), norm_coords
 

@@ -183,6 +183,43 @@ def cube_voxelize(features: torch.Tensor, coords: torch.Tensor, r: int) -> tuple
     return _voxelize(_L.ri_cube_voxelize_f32, "ri_cube_voxelize", features, coords, r, torch.int32)
 
 
+def _voxelize_edge(fn, what, features, coords, r, coord_dtype):
+    _req(features, "features", torch.float32); _req(coords, "coords", coord_dtype)
+    dev = _same_device(features, coords)
+    B, C, N = features.shape
+    s = r * r * r
+    with torch.cuda.device(dev):
+        out = torch.empty((B, C, s), dtype=torch.float32, device=dev)
+        ind = torch.empty((B, N), dtype=torch.int32, device=dev)
+        cnt = torch.empty((B, s), dtype=torch.int32, device=dev)
+        edge = torch.empty((B, 2 * C, N), dtype=torch.float32, device=dev)
+        ws = _workspace(dev, _L.ri_voxelize_workspace_bytes(B, N, r))
+        _check(fn(features.data_ptr(), coords.data_ptr(), B, C, N, r, out.data_ptr(), ind.data_ptr(), cnt.data_ptr(),
+                  edge.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), what)
+    return out, ind, cnt, edge
+
+
+@torch.library.custom_op("ri::sph_voxelize_edge", mutates_args=())
+def sph_voxelize_edge(features: torch.Tensor, coords: torch.Tensor, r: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    return _voxelize_edge(_L.ri_sph_voxelize_edge_f32, "ri_sph_voxelize_edge", features, coords, r, torch.float32)
+
+
+@torch.library.custom_op("ri::cube_voxelize_edge", mutates_args=())
+def cube_voxelize_edge(features: torch.Tensor, coords: torch.Tensor, r: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    return _voxelize_edge(_L.ri_cube_voxelize_edge_f32, "ri_cube_voxelize_edge", features, coords, r, torch.int32)
+
+
+def _vox_edge_fake(features, coords, r):
+    B, C, N = features.shape
+    s = r * r * r
+    return (features.new_empty((B, C, s)), features.new_empty((B, N), dtype=torch.int32),
+            features.new_empty((B, s), dtype=torch.int32), features.new_empty((B, 2 * C, N)))
+
+
+sph_voxelize_edge.register_fake(_vox_edge_fake)
+cube_voxelize_edge.register_fake(_vox_edge_fake)
+
+
 def _vox_fake(features, coords, r):
     B, C, N = features.shape
     s = r * r * r

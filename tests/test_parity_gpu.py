@@ -279,3 +279,97 @@ def test_error_behaviour(ri):
         torch.ops.ri.knn(xc, xc, 4)                      # non-contiguous, like CHECK_CONTIGUOUS
     with pytest.raises(RuntimeError):
         torch.ops.ri.cube_voxelize(torch.randn(1, 2, 8, device="cuda"), torch.zeros(1, 3, 8, device="cuda"), 4)  # float coords
+
+
+# ================================================================================================ fused forms
+@pytest.mark.parametrize("shape", ["spherical", "cube"])
+def test_voxelize_edge_fused_equals_two_step(ri, shape):
+    B, N, C, r = 6, 1024, 13, 32
+    pts = clouds(B, N, 61)
+    xyz = T(pts[:, :3].copy())
+    feat = torch.randn(B, C, N, device="cuda")
+    if shape == "spherical":
+        nc = sph_norm(xyz); nc[0, :, 7] = 0.0; nc[1, :, 9] = torch.tensor([0.0, 0.0, -0.3], device="cuda")   # undefined pts
+        out, ind, cnt = torch.ops.ri.sph_voxelize(feat, nc, r)
+        out2, ind2, cnt2, edge = torch.ops.ri.sph_voxelize_edge(feat, nc, r)
+        assert int((ind == -1).sum()) >= 2
+    else:
+        vc = torch.randint(0, r, (B, 3, N), device="cuda", dtype=torch.int32)
+        out, ind, cnt = torch.ops.ri.cube_voxelize(feat, vc, r)
+        out2, ind2, cnt2, edge = torch.ops.ri.cube_voxelize_edge(feat, vc, r)
+    assert torch.equal(out, out2) and torch.equal(ind, ind2) and torch.equal(cnt, cnt2)
+    assert torch.equal(edge, torch.ops.ri.voxel_edge_gather(out, feat, ind))
+
+
+def test_voxelize_many_points_per_tile(ri, oracle):
+    """All points inside one grid tile (more occupied cells per tile than the register cache holds) and heavy
+    multiplicity per cell."""
+    B, N, C, r = 2, 4096, 5, 32
+    vc = torch.zeros((B, 3, N), device="cuda", dtype=torch.int32)
+    vc[:, 0] = torch.randint(0, 2, (B, N), device="cuda")            # x in {0,1}: cells 0..2047, one tile
+    vc[:, 1] = torch.randint(0, 32, (B, N), device="cuda")
+    vc[:, 2] = torch.randint(0, 32, (B, N), device="cuda")
+    feat = torch.randn(B, C, N, device="cuda")
+    out, ind, cnt, edge = torch.ops.ri.cube_voxelize_edge(feat, vc, r)
+    oout, oind, ocnt = oracle.avg_voxelize(A(feat), A(vc), r)
+    assert np.array_equal(A(ind), oind) and np.array_equal(A(cnt), ocnt)
+    assert np.array_equal(A(out), oout)
+    assert np.array_equal(A(edge), oracle.voxel_edge_gather(oout, A(feat), oind))
+
+
+def test_prologue_bit_identical_to_torch(ri):
+    """The one-kernel coordinate prologue must reproduce the torch module shells bit for bit (given torch's mean)."""
+    L = ri._lib.lib
+    B, N, r = 16, 1024, 32
+    pts = T(clouds(B, N, 71))
+    pts[:, :3] *= 1.7                                               # push some points outside [-1,1] -> clamp path
+    xyz = pts[:, :3].contiguous()
+    mean = pts[:, :3, :].mean(2)
+    assert torch.equal(mean, xyz.mean(2)), "strided-view mean differs from contiguous mean"
+    st = torch.cuda.current_stream().cuda_stream
+    nc = torch.empty(B, 3, N, device="cuda"); vc = torch.empty(B, 3, N, device="cuda", dtype=torch.int32)
+    o_xyz = torch.empty(B, 3, N, device="cuda"); o_n = torch.empty(B, 3, N, device="cuda")
+    # cube, normalize=False / True
+    for shape, mod in ((0, ri.modules.Voxelization(r, normalize=False)), (1, ri.modules.Voxelization(r, normalize=True, eps=0))):
+        t = xyz - xyz.mean(2, keepdim=True)
+        if shape == 1:
+            t = t / (t.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + 0) + 0.5
+        else:
+            t = (t + 1) / 2.0
+        t = torch.clamp(t * r, 0, r - 1)
+        ok_modes = []
+        for mode in range(5):
+            assert L.ri_vox_prologue_f32(pts.data_ptr(), 6, mean.data_ptr(), B, N, r, shape, 0.0, mode, o_xyz.data_ptr(),
+                                         o_n.data_ptr(), nc.data_ptr(), vc.data_ptr(), st) == 0
+            if torch.equal(nc, t) and torch.equal(vc, torch.round(t).to(torch.int32)):
+                ok_modes.append(mode)
+        assert ri.FrontEnd.NORM_MODE in ok_modes, "cube shape %d: matching norm modes %s" % (shape, ok_modes)
+        assert torch.equal(o_xyz, xyz) and torch.equal(o_n, pts[:, 3:].contiguous())
+    # spherical
+    t = sph_norm(xyz)
+    ok_modes = []
+    for mode in range(5):
+        assert L.ri_vox_prologue_f32(pts.data_ptr(), 6, mean.data_ptr(), B, N, r, 2, 0.0, mode, None, None,
+                                     nc.data_ptr(), None, st) == 0
+        if torch.equal(nc, t):
+            ok_modes.append(mode)
+    assert ri.FrontEnd.NORM_MODE in ok_modes, "spherical: matching norm modes %s" % ok_modes
+
+
+def test_pvconv_fused_edge_gradients_match_unfused(ri):
+    """PVConv uses the fused voxelize+edge op; its gradients must equal the two-step composition's."""
+    torch.manual_seed(1)
+    B, N, C, r = 2, 256, 6, 8
+    xyz = T(clouds(B, N, 81)[:, :3].copy())
+    for shape in ("spherical", "cube"):
+        mod = ri.modules.Spherical_Voxelization(r) if shape == "spherical" else ri.modules.Voxelization(r, normalize=False)
+        f1 = torch.randn(B, C, N, device="cuda", requires_grad=True)
+        f2 = f1.detach().clone().requires_grad_(True)
+        grid1, ind1, _, edge1 = mod(f1, xyz, with_edge=True)
+        grid2, ind2, _ = mod(f2, xyz)
+        edge2 = ri.functional.voxel_edge_features(grid2, f2, ind2)
+        assert torch.equal(grid1, grid2) and torch.equal(edge1, edge2)
+        wg, we = torch.randn_like(grid1), torch.randn_like(edge1)
+        ((grid1 * wg).sum() + (edge1 * we).sum()).backward()
+        ((grid2 * wg).sum() + (edge2 * we).sum()).backward()
+        assert scaled_err(A(f1.grad), A(f2.grad)) <= 1e-5
