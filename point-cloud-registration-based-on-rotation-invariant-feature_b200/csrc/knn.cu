@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kQueriesPerCta)
 knn3_kernel(const float* __restrict__ queries, const float* __restrict__ refs, int n, int m, int k,
             float* __restrict__ dist, int* __restrict__ idx)
 {
-    __shared__ float4 sref[kRefTile];
+    extern __shared__ float4 sref[];                 // min(m, kRefTile) reference points
     const int b = blockIdx.y;
     const int i = blockIdx.x * kQueriesPerCta + threadIdx.x;
     const bool live = i < n;
@@ -151,11 +151,12 @@ int launch_knn(const float* queries, const float* refs, int B, int c, int n, int
 {
     if (B == 0 || n == 0) return RI_OK;
     dim3 grid((n + kQueriesPerCta - 1) / kQueriesPerCta, B);
+    const size_t smem = (size_t)(m < kRefTile ? (m > 0 ? m : 1) : kRefTile) * sizeof(float4);
     if (c == 3 && k <= 32) {
-        if (k <= 8) knn3_kernel<8><<<grid, kQueriesPerCta, 0, st>>>(queries, refs, n, m, k, dist, idx);
-        else if (k <= 16) knn3_kernel<16><<<grid, kQueriesPerCta, 0, st>>>(queries, refs, n, m, k, dist, idx);
-        else if (k <= 20) knn3_kernel<20><<<grid, kQueriesPerCta, 0, st>>>(queries, refs, n, m, k, dist, idx);
-        else knn3_kernel<32><<<grid, kQueriesPerCta, 0, st>>>(queries, refs, n, m, k, dist, idx);
+        if (k <= 8) knn3_kernel<8><<<grid, kQueriesPerCta, smem, st>>>(queries, refs, n, m, k, dist, idx);
+        else if (k <= 16) knn3_kernel<16><<<grid, kQueriesPerCta, smem, st>>>(queries, refs, n, m, k, dist, idx);
+        else if (k <= 20) knn3_kernel<20><<<grid, kQueriesPerCta, smem, st>>>(queries, refs, n, m, k, dist, idx);
+        else knn3_kernel<32><<<grid, kQueriesPerCta, smem, st>>>(queries, refs, n, m, k, dist, idx);
     } else {
         knn_generic_kernel<<<grid, kQueriesPerCta, 0, st>>>(queries, refs, c, n, m, k, dist, idx);
     }

@@ -40,7 +40,8 @@ constexpr int kSmallCloudMax = 4096;     // K1 sorts a whole cloud inside one CT
 constexpr int kTileCells = 8192;         // 32 KB of fp32 per tile
 constexpr int kRing = 3;                 // tiles in flight per CTA
 constexpr int kFillThreads = 256;
-constexpr int kSegCache = 4;             // occupied cells per thread whose table entries live in registers
+constexpr int kFillMaxRegs = 96;          // 2 CTAs/SM use 48K registers: leaves room for the k-NN CTAs of the other branch
+constexpr int kSegCache = 2;             // occupied cells per thread whose table entries live in registers
 constexpr unsigned kNoCell = 0xffffffffu;
 
 struct VoxWs {                            // per-cloud int32 workspace layout
@@ -214,9 +215,9 @@ __device__ __forceinline__ float seg_value(const SegRegs sg, int p, int C, int N
     return acc;
 }
 
-__global__ void __launch_bounds__(kFillThreads, 2)
+__global__ void __maxnreg__(kFillMaxRegs)
 vox_fill_kernel(const float* __restrict__ feat, const int* __restrict__ ws, int B, int C, int N, int s,
-                int tile_cells, int ntiles, int planes_per_item, int ngroups,
+                int tile_cells, int ntiles,
                 float* __restrict__ out, int* __restrict__ cnt, float* __restrict__ edge)
 {
     extern __shared__ __align__(128) float sring[];        // kRing tiles of tile_cells floats
@@ -228,7 +229,12 @@ vox_fill_kernel(const float* __restrict__ feat, const int* __restrict__ ws, int 
         reinterpret_cast<float4*>(sring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
-    const long long total = (long long)B * ntiles * ngroups;
+    // Work = the flattened sequence of (cloud, tile, plane) units, 32 KB of output each.  Every CTA takes one
+    // contiguous, equally long slice of it: perfectly balanced, and a CTA changes (cloud, tile) at most
+    // ceil(slice / planes) + 1 times, so the per-item table fetch is paid once or twice per CTA, not per group.
+    const long long total = (long long)B * ntiles * planes;
+    const long long u_begin = total * blockIdx.x / gridDim.x;
+    const long long u_end = total * (blockIdx.x + 1) / gridDim.x;
     int slot = 0;
     // The ring slots are never re-zeroed wholesale.  Between two bulk copies out of a slot only the occupied cells
     // of the tile are rewritten; when the CTA moves on to another (cloud, tile) the cells of the PREVIOUS item are
@@ -253,11 +259,11 @@ vox_fill_kernel(const float* __restrict__ feat, const int* __restrict__ ws, int 
             tile[__ldg(oldW + L.off_cell + sg) - old_cell_lo] = 0.f;
     };
 
-    for (long long item = blockIdx.x; item < total; item += gridDim.x) {
-        // item -> (cloud, tile, plane group); groups of one (cloud,tile) are adjacent so neighbouring CTAs
-        // share the occupied-cell table in L2.
-        const int g = (int)(item % ngroups);
-        const long long bt = item / ngroups;
+    for (long long u = u_begin; u < u_end;) {
+        const long long bt = u / planes;
+        const int p0 = (int)(u - bt * planes);
+        const int p1 = (int)min((long long)planes, p0 + (u_end - u));
+        u += p1 - p0;
         const int t = (int)(bt % ntiles);
         const int b = (int)(bt / ntiles);
         const int* W = ws + (size_t)b * L.stride;
@@ -265,7 +271,6 @@ vox_fill_kernel(const float* __restrict__ feat, const int* __restrict__ ws, int 
         const int cell_lo = t * tile_cells;
         const int ncell = min(tile_cells, s - cell_lo);
         const int sA = __ldg(W + L.off_tile + t), sB = __ldg(W + L.off_tile + t + 1);
-        const int p0 = g * planes_per_item, p1 = min(planes, p0 + planes_per_item);
 
         if (curW != nullptr) {
             if (stale > 0 || prev_planes < kRing) {
@@ -307,7 +312,7 @@ vox_fill_kernel(const float* __restrict__ feat, const int* __restrict__ ws, int 
         extra_lo = min(sB, sA + kSegCache * kFillThreads); extra_hi = sB; cur_cell_lo = cell_lo; curW = W;
         prev_planes = p1 - p0;
 
-        // undefined points of this cloud (ind == -1): edge rows are (0, feat); done once per plane group
+        // undefined points of this cloud (ind == -1): edge rows are (0, feat); done by whoever owns tile 0's planes
         if (edge != nullptr && t == 0) {
             const int nvalid = __ldg(W + L.off_meta + 1);
             for (int u = nvalid + tid; u < N; u += kFillThreads) {
@@ -423,12 +428,6 @@ VoxPlan vox_plan(int N, int r, const void* out, const void* cnt)
     return p;
 }
 
-int env_int(const char* name, int dflt)
-{
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
 template <bool SPH>
 int voxelize_impl(const float* feat, const void* coords, int B, int C, int N, int r,
                   float* out, int* ind, int* cnt, float* edge, void* workspace, size_t ws_bytes, cudaStream_t st)
@@ -456,21 +455,11 @@ int voxelize_impl(const float* feat, const void* coords, int B, int C, int N, in
         const size_t smem2 = (size_t)kRing * plan.tile_cells * sizeof(float);
         e = cudaFuncSetAttribute(vox_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         if (e != cudaSuccess) return (int)e;
-        const int planes = C + 1;
-        const long long bt = (long long)B * plan.ntiles;
+        const long long units = (long long)B * plan.ntiles * (C + 1);
         long long grid = 2LL * sms;
-        static const int items_per_cta = env_int("RI_VOX_ITEMS_PER_CTA", 4);
-        static const int min_planes = env_int("RI_VOX_MIN_PLANES", 6);
-        long long want_groups = ((long long)items_per_cta * grid + bt - 1) / bt;   // a few items per CTA for balance
-        if (want_groups < 1) want_groups = 1;
-        if (want_groups > planes) want_groups = planes;
-        int ppi = (int)((planes + want_groups - 1) / want_groups);
-        if (ppi < min_planes) ppi = min_planes < planes ? min_planes : planes;
-        const int ngroups = (planes + ppi - 1) / ppi;
-        const long long total = bt * ngroups;
-        if (grid > total) grid = total;
+        if (grid > units) grid = units;
         vox_fill_kernel<<<(unsigned)grid, kFillThreads, smem2, st>>>(feat, ws, B, C, N, s, plan.tile_cells, plan.ntiles,
-                                                                     ppi, ngroups, out, cnt, edge);
+                                                                     out, cnt, edge);
         RI_LAUNCH_CHECK();
         return RI_OK;
     }
