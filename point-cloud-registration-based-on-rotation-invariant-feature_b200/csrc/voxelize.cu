@@ -40,6 +40,7 @@ constexpr int kSmallCloudMax = 4096;     // K1 sorts a whole cloud inside one CT
 constexpr int kTileCells = 8192;         // 32 KB of fp32 per tile
 constexpr int kRing = 3;                 // tiles in flight per CTA
 constexpr int kFillThreads = 256;
+constexpr int kPlaneBatch = 8;            // channel planes whose gathers are issued together
 constexpr int kFillMaxRegs = 96;          // 2 CTAs/SM use 48K registers: leaves room for the k-NN CTAs of the other branch
 constexpr int kSegCache = 2;             // occupied cells per thread whose table entries live in registers
 constexpr unsigned kNoCell = 0xffffffffu;
@@ -324,50 +325,79 @@ vox_fill_kernel(const float* __restrict__ feat, const int* __restrict__ ws, int 
             }
         }
 
-        float val[kSegCache];
-        auto compute = [&](int p) {
-            const float* Fp = feat + ((size_t)b * C + (p < C ? p : 0)) * N;
-            float* er = (edge != nullptr && p < C) ? edge + ((size_t)b * 2 * C + p) * N : nullptr;
-            float* ec = (edge != nullptr && p < C) ? edge + ((size_t)b * 2 * C + C + p) * N : nullptr;
+        // Planes are handled in batches of kPlaneBatch: the gathers of a whole batch (independent loads, one per
+        // plane and point) are issued together, so their latency is paid once per batch, not once per 32 KB tile.
+        for (int pb = p0; pb < p1; pb += kPlaneBatch) {
+            float val[kSegCache][kPlaneBatch];
 #pragma unroll
-            for (int q = 0; q < kSegCache; ++q)
-                if (seg[q].cnt > 0) val[q] = seg_value(seg[q], p, C, N, Fp, pid, er, ec);
-        };
-        compute(p0);
-        for (int p = p0; p < p1; ++p) {
-            float* tile = sring + slot * tile_cells;
-            if (tid == 0) ri_bulk_wait_read<kRing - 1>();  // the copy that last used this slot has left smem
-            __syncthreads();
-            if (stale > 0) {                                // first reuse of this slot since the item switch
-                unpatch_slot(tile);
-                --stale;
-                __syncthreads();                            // an old cell may coincide with a new one of another thread
-            }
+            for (int q = 0; q < kSegCache; ++q) {
+                if (seg[q].cnt <= 0) continue;
+                const float inv = __fdiv_rn(1.0f, (float)seg[q].cnt);                       // vox.cu:66
 #pragma unroll
-            for (int q = 0; q < kSegCache; ++q)
-                if (seg[q].cnt > 0) tile[seg[q].off] = val[q];
-            if (extra_lo < extra_hi) {                      // cells beyond the register cache: direct path
-                const float* Fp = feat + ((size_t)b * C + (p < C ? p : 0)) * N;
-                float* er = (edge != nullptr && p < C) ? edge + ((size_t)b * 2 * C + p) * N : nullptr;
-                float* ec = (edge != nullptr && p < C) ? edge + ((size_t)b * 2 * C + C + p) * N : nullptr;
-                for (int sg = extra_lo + tid; sg < extra_hi; sg += kFillThreads) {
-                    SegRegs x;
-                    x.off = __ldg(W + L.off_cell + sg) - cell_lo;
-                    x.st = __ldg(W + L.off_start + sg);
-                    x.cnt = __ldg(W + L.off_start + sg + 1) - x.st;
-                    tile[x.off] = seg_value(x, p, C, N, Fp, pid, er, ec);
+                for (int j = 0; j < kPlaneBatch; ++j) val[q][j] = 0.f;
+                for (int u = seg[q].st; u < seg[q].st + seg[q].cnt; ++u) {                  // ascending point order
+                    const int i = __ldg(pid + u);
+                    float f[kPlaneBatch];
+#pragma unroll
+                    for (int j = 0; j < kPlaneBatch; ++j)
+                        f[j] = (pb + j < min(p1, C)) ? __ldg(feat + ((size_t)b * C + pb + j) * N + i) : 0.f;
+#pragma unroll
+                    for (int j = 0; j < kPlaneBatch; ++j)
+                        val[q][j] = __fadd_rn(val[q][j], __fmul_rn(f[j], inv));             // vox.cu:68-70
                 }
+                if (edge != nullptr) {
+                    for (int u = seg[q].st; u < seg[q].st + seg[q].cnt; ++u) {
+                        const int i = __ldg(pid + u);
+#pragma unroll
+                        for (int j = 0; j < kPlaneBatch; ++j)
+                            if (pb + j < min(p1, C)) {
+                                const float f = __ldg(feat + ((size_t)b * C + pb + j) * N + i);
+                                edge[((size_t)b * 2 * C + pb + j) * N + i] = __fsub_rn(f, val[q][j]);
+                                edge[((size_t)b * 2 * C + C + pb + j) * N + i] = f;
+                            }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kPlaneBatch; ++j)
+                    if (pb + j >= C) val[q][j] = __int_as_float(seg[q].cnt);               // the count plane
             }
-            ri_fence_proxy_async_smem();
-            __syncthreads();
-            if (tid == 0) {
-                void* dst = (p < C) ? (void*)(out + ((size_t)b * C + p) * s + cell_lo)
-                                    : (void*)(cnt + (size_t)b * s + cell_lo);
-                ri_bulk_store(dst, tile, (uint32_t)ncell * 4u);
-                ri_bulk_commit();
+#pragma unroll
+            for (int j = 0; j < kPlaneBatch; ++j) {
+                const int p = pb + j;
+                if (p >= p1) break;
+                float* tile = sring + slot * tile_cells;
+                if (tid == 0) ri_bulk_wait_read<kRing - 1>();  // the copy that last used this slot has left smem
+                __syncthreads();
+                if (stale > 0) {                                // first reuse of this slot since the item switch
+                    unpatch_slot(tile);
+                    --stale;
+                    __syncthreads();                            // an old cell may coincide with a new one of another thread
+                }
+#pragma unroll
+                for (int q = 0; q < kSegCache; ++q)
+                    if (seg[q].cnt > 0) tile[seg[q].off] = val[q][j];
+                if (extra_lo < extra_hi) {                      // cells beyond the register cache: direct path
+                    const float* Fp = feat + ((size_t)b * C + (p < C ? p : 0)) * N;
+                    float* er = (edge != nullptr && p < C) ? edge + ((size_t)b * 2 * C + p) * N : nullptr;
+                    float* ec = (edge != nullptr && p < C) ? edge + ((size_t)b * 2 * C + C + p) * N : nullptr;
+                    for (int sg = extra_lo + tid; sg < extra_hi; sg += kFillThreads) {
+                        SegRegs x;
+                        x.off = __ldg(W + L.off_cell + sg) - cell_lo;
+                        x.st = __ldg(W + L.off_start + sg);
+                        x.cnt = __ldg(W + L.off_start + sg + 1) - x.st;
+                        tile[x.off] = seg_value(x, p, C, N, Fp, pid, er, ec);
+                    }
+                }
+                ri_fence_proxy_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    void* dst = (p < C) ? (void*)(out + ((size_t)b * C + p) * s + cell_lo)
+                                        : (void*)(cnt + (size_t)b * s + cell_lo);
+                    ri_bulk_store(dst, tile, (uint32_t)ncell * 4u);
+                    ri_bulk_commit();
+                }
+                slot = (slot + 1 == kRing) ? 0 : slot + 1;
             }
-            slot = (slot + 1 == kRing) ? 0 : slot + 1;
-            if (p + 1 < p1) compute(p + 1);                 // gathers of the next plane overlap this plane's store
         }
     }
     if (tid == 0) ri_bulk_wait<0>();
