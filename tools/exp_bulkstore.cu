@@ -4,14 +4,19 @@
 #include <cuda_runtime.h>
 __device__ __forceinline__ uint32_t smem_u32(const void* p){ return (uint32_t)__cvta_generic_to_shared(p); }
 template<int RING>
-__global__ void bulk_kernel(float* out, long long ntiles, int tile_floats, int sync_mode)
+__global__ void bulk_kernel(float* out, long long ntiles, int tile_floats, int sync_mode, int order=0)
 {
     extern __shared__ __align__(128) float s[];
     for (int i = threadIdx.x; i < RING*tile_floats; i += blockDim.x) s[i] = 0.f;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     int slot = 0;
-    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    long long lo = 0, hi = ntiles, step = 1;
+    if (order == 0) { lo = blockIdx.x; step = gridDim.x; }
+    else { lo = ntiles * blockIdx.x / gridDim.x; hi = ntiles * (blockIdx.x + 1) / gridDim.x; }
+    for (long long tt = lo; tt < hi; tt += step) {
+        long long t = tt;
+        if (order == 2) { long long plane = tt % 72, bt = tt / 72; t = (bt / 4) * 288 + plane * 4 + (bt % 4); if (t >= ntiles) t = tt; }
         if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(RING-1) : "memory");
         if (sync_mode) { __syncthreads(); s[slot*tile_floats + threadIdx.x] = (float)t; asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); __syncthreads(); }
         if (threadIdx.x == 0) {
@@ -55,6 +60,12 @@ int main(){
         cudaFuncSetAttribute(bulk_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         char nm[128]; snprintf(nm,128,"bulk ring6 tile=%dKB ctas/sm=%d sync=1", tile_kb, cps);
         run(nm, [&](float* b){ bulk_kernel<6><<<sms*cps,256,sm>>>(b, nt, tf, 1); });
+    }
+    for (int order : {0, 1, 2}) {
+        int tf = 32*256; long long nt = bytes/4/tf; size_t sm = 3*tf*4;
+        cudaFuncSetAttribute(bulk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        char nm[128]; snprintf(nm,128,"bulk ring3 tile=32KB ctas/sm=2 sync=1 order=%d", order);
+        run(nm, [&](float* b){ bulk_kernel<3><<<sms*2,256,sm>>>(b, nt, tf, 1, order); });
     }
     for (int mult : {4, 8, 16, 32}) { char nm[128]; snprintf(nm,128,"st.global.v4 grid=%dxSMs x256", mult);
         run(nm, [&](float* b){ st_kernel<<<sms*mult,256>>>((float4*)b, bytes/16); }); }
