@@ -126,6 +126,21 @@ int ri_devox_backward_f32(const float* grad_y, const int* inds, const float* wgt
 int ri_voxel_edge_gather_f32(const float* avg, const float* feat, const int* inds, int B, int C, int N, int s,
                              float* out, void* stream);
 
+/* ---- mutual-nearest-neighbour descriptor matching (datasets/deepgmr_mn40.py:232-244) ---------------------
+ * find_correspondence_one_pair for P independent (source, target) pairs.
+ * desc1, desc2: fp32 descriptors, channel-major [P,C,n1] / [P,C,n2] (what the feature extractor emits,
+ * pvcnn_classify.py:345) when point_major == 0, or point-major [P,n1,C] / [P,n2,C] (the numpy layout the
+ * reference's meter passes, deepgmr_mn40.py:121) when point_major != 0.
+ *   diff[i,j] = |f1_i|^2 + |f2_j|^2 - 2 f1_i.f2_j           (3xTF32 split-precision tcgen05 contraction)
+ *   corr12 [P,n1] = argmin_j diff, corr21 [P,n2] = argmin_i diff   (lowest index on ties, as np.argmin)
+ *   dist12 [P,n1] = diff[i, corr12[i]] recomputed as an fp32 FMA chain
+ *   idx1, idx2 [P,n1]: the mutual matches (corr21[corr12[i]] == i) in ascending i, count [P] of them, -1 beyond.
+ * workspace >= ri_mutual_nn_workspace_bytes(P, C, n1, n2) bytes of device memory. */
+size_t ri_mutual_nn_workspace_bytes(int P, int C, int n1, int n2);
+int ri_mutual_nn_tf32x3(const float* desc1, const float* desc2, int P, int C, int n1, int n2, int point_major,
+                        int* corr12, int* corr21, float* dist12, int* idx1, int* idx2, int* count,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,6 @@ from . import ops             # noqa: F401  registers torch.ops.ri.*
 from .backend import _backend  # noqa: F401
 from . import functional, modules  # noqa: F401
 from .frontend import FrontEnd  # noqa: F401
-from . import shard, synth     # noqa: F401
+from . import shard, synth, matcher  # noqa: F401
 
 __version__ = '0.1.0'

@@ -1,0 +1,445 @@
+// matcher.cu — mutual-nearest-neighbour descriptor matching on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Replaces  find_correspondence_one_pair  (/root/reference/datasets/deepgmr_mn40.py:232-244; duplicated in
+// deepgmr_partial.py:335-347, mn40_hdf.py:466-477, ...), which the registration meters call per pair on the CPU
+// after a .cpu().numpy() hop (deepgmr_mn40.py:88,200):
+//     diff = ||f1||^2[:,None] + ||f2||^2[None,:] - 2 f1 f2^T ;  c1 = argmin(diff, 1) ;  c2 = argmin(diff, 0)
+//     mask = c2[c1] == arange(n1) ;  return arange(n1)[mask], c1[mask]
+//
+// B200 design.  The n1 x n2 x C contraction is the only O(n^2 C) term, so it goes on tcgen05; the n1 x n2 matrix is
+// never written anywhere: the epilogue reads the fp32 accumulator tile out of TMEM, adds the norms and reduces it to
+// one (distance, index) key per row and per column on the spot.
+//
+//   * Precision: a single tf32/bf16 pass cannot hold the 1e-5 contract (nor stable argmins), so the product is the
+//     3xTF32 split  a = a_hi + a_lo  (a_hi = a with the low 13 mantissa bits cleared — representable in tf32 whatever
+//     the hardware does with the low bits —, a_lo = a - a_hi, exact in fp32),  a.b ~ hi.hi + hi.lo + lo.hi, fp32
+//     accumulation in TMEM: ~2^-22 relative per product, the order of sgemm's own rounding.
+//   * match_prep     per cloud: squared norms (accumulated in fp64, rounded once), the hi/lo split, and a re-tiling into
+//                    UMMA "canonical K-major, no swizzle" core-matrix images  T[kc][plane][row/8][k16/4][row%8][4 floats]
+//                    (kc = 16-channel chunk, plane = hi|lo).  An operand tile of R rows x 16 channels is then ONE
+//                    contiguous R*64-byte block, so the GEMM kernel stages operands with plain cp.async.bulk copies
+//                    (TMA engine, no tensor maps) and describes them with LBO = 128 B, SBO = 512 B.
+//   * match_gemm     one CTA per 128 x 256 tile of a pair's distance matrix, 192 threads, warp-specialised:
+//                      warp 0 / lane 0   producer: 4-stage ring of 48 KB stages, mbarrier complete_tx
+//                      warp 1            TMEM allocator; lane 0 issues tcgen05.mma.kind::tf32 (M128 N256 K8), 6 per stage,
+//                                        tcgen05.commit releases the stage / publishes the accumulator
+//                      warps 2-5         epilogue: tcgen05.ld 32 columns at a time, d = (n1 + n2) - 2 acc, row argmin in
+//                                        registers, column argmin with redux.sync + ballot, merged across tiles by
+//                                        64-bit atomicMin on packed keys (ordered(d) << 32 | index): lowest index
+//                                        wins ties, as np.argmin does.
+//   * match_finish   per pair: unpack c1/c2, mutual mask, ordered compaction (idx1, idx2, count), and the distance of
+//                    every row's match recomputed as an fp32 FMA chain (what is reported, not the 3xTF32 value).
+#include "ri_common.cuh"
+
+namespace {
+
+constexpr int kTileM = 128;          // rows of f1 per CTA (TMEM lanes)
+constexpr int kTileN = 256;          // rows of f2 per CTA (TMEM columns)
+constexpr int kChunkK = 16;          // channels per pipeline stage (2 UMMA K-steps of 8 tf32)
+constexpr int kStages = 4;
+constexpr int kGemmThreads = 192;
+constexpr int kRowBytes = kChunkK * 4;                       // 64 B of one row in one chunk
+constexpr int kABytes = kTileM * kRowBytes;                  // 8 KB  (one plane)
+constexpr int kBBytes = kTileN * kRowBytes;                  // 16 KB (one plane)
+constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;       // 48 KB
+constexpr unsigned kLBO = 128, kSBO = 512;                   // see the image layout above
+
+__host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct MatchWs {                     // byte offsets inside the workspace
+    size_t img1, img2, nrm1, nrm2, rowkey, colkey, total;
+    int n1p, n2p, Cp;
+};
+__host__ __device__ inline MatchWs match_ws_layout(int P, int C, int n1, int n2)
+{
+    MatchWs w;
+    w.n1p = round_up(n1 > 0 ? n1 : 1, kTileN);        // both padded to the 256-row granule of match_prep
+    w.n2p = round_up(n2 > 0 ? n2 : 1, kTileN);
+    w.Cp = round_up(C > 0 ? C : 1, kChunkK);
+    size_t o = 0;
+    w.img1 = o; o += (size_t)P * w.n1p * w.Cp * 2 * sizeof(float);
+    w.img2 = o; o += (size_t)P * w.n2p * w.Cp * 2 * sizeof(float);
+    w.nrm1 = o; o += (size_t)P * w.n1p * sizeof(float);
+    w.nrm2 = o; o += (size_t)P * w.n2p * sizeof(float);
+    o = (o + 15) / 16 * 16;
+    w.rowkey = o; o += (size_t)P * w.n1p * sizeof(unsigned long long);
+    w.colkey = o; o += (size_t)P * w.n2p * sizeof(unsigned long long);
+    w.total = o;
+    return w;
+}
+
+__device__ __forceinline__ unsigned ordered_u32(float f)
+{
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ------------------------------------------------------------------------------------------------ match_prep
+// One CTA = (cloud, tile of 256 rows).  Walks the channel chunks; per chunk the 16 x 256 block goes through shared
+// memory so that global reads are coalesced along the source's contiguous axis and image writes are 16-byte chunks in
+// address order.
+constexpr int kPrepRows = 256;
+constexpr int kPrepLd = kPrepRows + 2;                       // 4*q*ld mod 32 = {0,8,16,24}: conflict-free chunk reads
+
+__global__ void __launch_bounds__(1024)
+match_prep_kernel(const float* __restrict__ desc, int C, int n, int npad, int Cp, int point_major,
+                  float* __restrict__ img, float* __restrict__ nrm, unsigned long long* __restrict__ key)
+{
+    __shared__ float s[kChunkK * kPrepLd];
+    const int cloud = blockIdx.y;
+    const int r0 = blockIdx.x * kPrepRows;
+    const int u = threadIdx.x;                               // 16-byte chunk id inside the (256 rows x 16 ch) block
+    const int i_loc = ((u >> 5) << 3) | (u & 7);
+    const int q = (u >> 3) & 3;
+    const float* D = desc + (size_t)cloud * C * n;
+    float* I = img + (size_t)cloud * npad * Cp * 2;
+    const size_t plane = (size_t)npad * kChunkK;             // floats per (chunk, plane)
+    double acc = 0.0;
+
+    for (int kc = 0; kc < Cp / kChunkK; ++kc) {
+        __syncthreads();
+        if (!point_major) {                                  // [C, n]: lanes walk rows (contiguous)
+            for (int e = u; e < kChunkK * kPrepRows; e += 1024) {
+                const int c = e >> 8, i = e & 255;
+                const int gc = kc * kChunkK + c, gi = r0 + i;
+                s[c * kPrepLd + i] = (gc < C && gi < n) ? D[(size_t)gc * n + gi] : 0.f;
+            }
+        } else {                                             // [n, C]: lanes walk channels (contiguous)
+            for (int e = u; e < kChunkK * kPrepRows; e += 1024) {
+                const int c = e & 15, i = e >> 4;
+                const int gc = kc * kChunkK + c, gi = r0 + i;
+                s[c * kPrepLd + i] = (gc < C && gi < n) ? D[(size_t)gi * C + gc] : 0.f;
+            }
+        }
+        __syncthreads();
+        float4 hi, lo;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            v[e] = s[(4 * q + e) * kPrepLd + i_loc];
+            acc = fma((double)v[e], (double)v[e], acc);
+        }
+        hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u); lo.x = __fsub_rn(v[0], hi.x);
+        hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u); lo.y = __fsub_rn(v[1], hi.y);
+        hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u); lo.z = __fsub_rn(v[2], hi.z);
+        hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u); lo.w = __fsub_rn(v[3], hi.w);
+        // image offset of row (r0 + i_loc), k-core q :  ((row / 8) * 4 + q) * 32 + (row % 8) * 4  floats
+        float* dst = I + (size_t)kc * 2 * plane + (size_t)(r0 >> 3) * 128 + (size_t)u * 4;
+        *reinterpret_cast<float4*>(dst) = hi;
+        *reinterpret_cast<float4*>(dst + plane) = lo;
+    }
+    // squared norm of row i_loc: the four k-core partials sit in lanes u ^ 8, u ^ 16, u ^ 24
+    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    if (q == 0) {
+        nrm[(size_t)cloud * npad + r0 + i_loc] = (float)acc;
+        key[(size_t)cloud * npad + r0 + i_loc] = ~0ull;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major, no swizzle: start address, leading-dimension (K) byte offset, stride-dimension (M/N) byte offset,
+// descriptor version 1 (Blackwell) in bits 46-47.  (cute/arch/mma_sm100_desc.hpp::SmemDescriptor)
+// (Pinned on a B200: with the two strides exchanged every argmin is wrong.)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr)
+{
+    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)(kLBO >> 4) << 16) | ((uint64_t)(kSBO >> 4) << 32) |
+           (1ull << 46);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, N = 256, M = 128 (cute/arch/mma_sm100_desc.hpp::InstrDescriptor)
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
+                            ((uint32_t)(kTileM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ match_gemm
+struct GemmSmem {                                            // after the stage ring
+    unsigned long long colkey[4][kTileN];                    // per epilogue warp, per column
+    float n2[kTileN];
+    unsigned long long full[kStages], empty[kStages], accum;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
+                  const float* __restrict__ nrm1, const float* __restrict__ nrm2,
+                  int n1, int n2, int n1p, int n2p, int Cp,
+                  unsigned long long* __restrict__ rowkey, unsigned long long* __restrict__ colkey)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    GemmSmem* S = reinterpret_cast<GemmSmem*>(smem + (size_t)kStages * kStageBytes);
+    const uint32_t ring = ri_smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pair = blockIdx.z, m0 = blockIdx.y * kTileM, c0 = blockIdx.x * kTileN;
+    const int nk = Cp / kChunkK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(ri_smem_u32(&S->full[s]), 1);
+            mbar_init(ri_smem_u32(&S->empty[s]), 1);
+        }
+        mbar_init(ri_smem_u32(&S->accum), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        ri_fence_proxy_async_smem();
+    }
+    if (warp == 1) {                                         // TMEM: 256 fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(ri_smem_u32(&S->tmem_base)), "r"((uint32_t)kTileN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {
+        const int t = threadIdx.x - 64;
+        for (int j = t; j < kTileN; j += 128) S->n2[j] = nrm2[(size_t)pair * n2p + c0 + j];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {                                     // ---- producer
+            const uint8_t* A = reinterpret_cast<const uint8_t*>(img1) + (size_t)pair * n1p * Cp * 8;
+            const uint8_t* B = reinterpret_cast<const uint8_t*>(img2) + (size_t)pair * n2p * Cp * 8;
+            const size_t planeA = (size_t)n1p * kRowBytes, planeB = (size_t)n2p * kRowBytes;
+            for (int kc = 0; kc < nk; ++kc) {
+                const int s = kc % kStages;
+                const uint32_t ph = (kc / kStages) & 1;
+                mbar_wait(ri_smem_u32(&S->empty[s]), ph ^ 1);
+                const uint32_t full = ri_smem_u32(&S->full[s]);
+                mbar_expect_tx(full, kStageBytes);
+                const uint32_t dst = ring + s * kStageBytes;
+                const uint8_t* a = A + (size_t)kc * 2 * planeA + (size_t)m0 * kRowBytes;
+                const uint8_t* b = B + (size_t)kc * 2 * planeB + (size_t)c0 * kRowBytes;
+                bulk_g2s(dst, a, kABytes, full);
+                bulk_g2s(dst + kABytes, a + planeA, kABytes, full);
+                bulk_g2s(dst + 2 * kABytes, b, kBBytes, full);
+                bulk_g2s(dst + 2 * kABytes + kBBytes, b + planeB, kBBytes, full);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                     // ---- MMA issuer
+            for (int kc = 0; kc < nk; ++kc) {
+                const int s = kc % kStages;
+                const uint32_t ph = (kc / kStages) & 1;
+                mbar_wait(ri_smem_u32(&S->full[s]), ph);
+                tc_fence_after();
+                const uint32_t base = ring + s * kStageBytes;
+#pragma unroll
+                for (int ks = 0; ks < kChunkK / 8; ++ks) {
+                    const uint32_t koff = ks * 2 * kLBO;     // one K-step = two 16-byte k-cores
+                    const uint64_t a_hi = smem_desc(base + koff);
+                    const uint64_t a_lo = smem_desc(base + kABytes + koff);
+                    const uint64_t b_hi = smem_desc(base + 2 * kABytes + koff);
+                    const uint64_t b_lo = smem_desc(base + 2 * kABytes + kBBytes + koff);
+                    tc_mma_tf32(tmem, a_lo, b_hi, kIdesc, (kc | ks) != 0);      // small terms first
+                    tc_mma_tf32(tmem, a_hi, b_lo, kIdesc, 1);
+                    tc_mma_tf32(tmem, a_hi, b_hi, kIdesc, 1);
+                }
+                tc_commit(ri_smem_u32(&S->empty[s]));        // stage reusable once these MMAs have read it
+            }
+            tc_commit(ri_smem_u32(&S->accum));               // accumulator complete
+        }
+    } else {                                                 // ---- epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1)
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const int gi = m0 + row;
+        const bool row_ok = gi < n1;
+        const float na = nrm1[(size_t)pair * n1p + gi];
+        mbar_wait(ri_smem_u32(&S->accum), 0);
+        tc_fence_after();
+        float best = 0.f; int best_j = -1;
+        for (int cc = 0; cc < kTileN; cc += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)cc, v);
+            unsigned long long mine = ~0ull;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const int j = c0 + cc + e;
+                const float d = __fmaf_rn(-2.0f, __uint_as_float(v[e]), __fadd_rn(na, S->n2[cc + e]));
+                if (j < n2 && (best_j < 0 || d < best)) { best = d; best_j = j; }
+                const unsigned key = row_ok ? ordered_u32(d) : 0xffffffffu;
+                const unsigned mn = __reduce_min_sync(0xffffffffu, key);
+                const unsigned who = __ballot_sync(0xffffffffu, key == mn);
+                if (lane == e)
+                    mine = ((unsigned long long)mn << 32) | (unsigned)(m0 + qd * 32 + (__ffs(who) - 1));
+            }
+            S->colkey[qd][cc + lane] = mine;
+        }
+        if (row_ok && best_j >= 0)
+            atomicMin(rowkey + (size_t)pair * n1p + gi, ((unsigned long long)ordered_u32(best) << 32) | (unsigned)best_j);
+        asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps
+        const int t = threadIdx.x - 64;
+        for (int j = t; j < kTileN; j += 128) {
+            if (c0 + j >= n2) continue;
+            unsigned long long k0 = S->colkey[0][j];
+            const unsigned long long k1 = S->colkey[1][j], k2 = S->colkey[2][j], k3 = S->colkey[3][j];
+            k0 = k1 < k0 ? k1 : k0; k0 = k2 < k0 ? k2 : k0; k0 = k3 < k0 ? k3 : k0;
+            if ((unsigned)(k0 >> 32) != 0xffffffffu) atomicMin(colkey + (size_t)pair * n2p + c0 + j, k0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)kTileN) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ match_finish
+// One CTA per pair.  corr12[i] = argmin_j, corr21[j] = argmin_i, dist12[i] = fp32 distance of (i, corr12[i]) recomputed
+// with an FMA chain over the channels, (idx1, idx2)[0..count) = the mutual matches in ascending i, -1 beyond.
+constexpr int kFinThreads = 512;
+__global__ void __launch_bounds__(kFinThreads)
+match_finish_kernel(const float* __restrict__ d1, const float* __restrict__ d2, int C, int n1, int n2, int n1p, int n2p,
+                    int point_major, const float* __restrict__ nrm1, const float* __restrict__ nrm2,
+                    const unsigned long long* __restrict__ rowkey, const unsigned long long* __restrict__ colkey,
+                    int* __restrict__ corr12, int* __restrict__ corr21, float* __restrict__ dist12,
+                    int* __restrict__ idx1, int* __restrict__ idx2, int* __restrict__ count)
+{
+    __shared__ int swarp[kFinThreads / 32];
+    __shared__ int sbase;
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned long long* RK = rowkey + (size_t)p * n1p;
+    const unsigned long long* CK = colkey + (size_t)p * n2p;
+    for (int j = tid; j < n2; j += kFinThreads) corr21[(size_t)p * n2 + j] = (int)(unsigned)(CK[j] & 0xffffffffu);
+    const float* F1 = d1 + (size_t)p * C * n1;
+    const float* F2 = d2 + (size_t)p * C * n2;
+    if (tid == 0) sbase = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n1; i0 += kFinThreads) {
+        const int i = i0 + tid;
+        int j = -1, mutual = 0;
+        if (i < n1) {
+            j = (int)(unsigned)(RK[i] & 0xffffffffu);
+            const bool sane = (unsigned)j < (unsigned)n2;            // false only if every distance of the row was NaN
+            if (!sane) j = 0;
+            corr12[(size_t)p * n1 + i] = j;
+            mutual = (sane && (int)(unsigned)(CK[j] & 0xffffffffu) == i) ? 1 : 0;
+            float dot = 0.f;
+            if (point_major) {
+                const float* a = F1 + (size_t)i * C; const float* b = F2 + (size_t)j * C;
+                for (int c = 0; c < C; ++c) dot = __fmaf_rn(a[c], b[c], dot);
+            } else {
+                for (int c = 0; c < C; ++c) dot = __fmaf_rn(F1[(size_t)c * n1 + i], F2[(size_t)c * n2 + j], dot);
+            }
+            dist12[(size_t)p * n1 + i] =
+                __fmaf_rn(-2.0f, dot, __fadd_rn(nrm1[(size_t)p * n1p + i], nrm2[(size_t)p * n2p + j]));
+        }
+        // ordered compaction of the mutual matches
+        const unsigned bal = __ballot_sync(0xffffffffu, mutual);
+        const int before = __popc(bal & ((1u << lane) - 1));
+        if (lane == 0) swarp[wid] = __popc(bal);
+        __syncthreads();
+        int off = sbase;
+        for (int w = 0; w < wid; ++w) off += swarp[w];
+        if (mutual) { idx1[(size_t)p * n1 + off + before] = i; idx2[(size_t)p * n1 + off + before] = j; }
+        __syncthreads();
+        if (tid == 0) { int tot = 0; for (int w = 0; w < kFinThreads / 32; ++w) tot += swarp[w]; sbase += tot; }
+        __syncthreads();
+    }
+    const int total = sbase;
+    for (int i = total + tid; i < n1; i += kFinThreads) { idx1[(size_t)p * n1 + i] = -1; idx2[(size_t)p * n1 + i] = -1; }
+    if (tid == 0) count[p] = total;
+}
+
+}  // namespace
+
+extern "C" size_t ri_mutual_nn_workspace_bytes(int P, int C, int n1, int n2)
+{
+    if (P <= 0 || C <= 0 || n1 <= 0 || n2 <= 0) return 16;
+    return match_ws_layout(P, C, n1, n2).total + 1024;
+}
+
+extern "C" int ri_mutual_nn_tf32x3(const float* desc1, const float* desc2, int P, int C, int n1, int n2, int point_major,
+                                   int* corr12, int* corr21, float* dist12, int* idx1, int* idx2, int* count,
+                                   void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (P < 0 || C <= 0 || n1 < 0 || n2 < 0) return RI_ERR_BAD_ARG;
+    if (P > 65535) return RI_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (P == 0) return RI_OK;
+    if (n1 == 0 || n2 == 0) {                                // nothing can match
+        cudaError_t e = cudaMemsetAsync(count, 0, (size_t)P * sizeof(int), st);
+        return e == cudaSuccess ? RI_OK : (int)e;
+    }
+    const MatchWs L = match_ws_layout(P, C, n1, n2);
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
+    if (workspace == nullptr || (size_t)(ws - reinterpret_cast<uint8_t*>(workspace)) + L.total > workspace_bytes)
+        return RI_ERR_WORKSPACE;
+    float* img1 = reinterpret_cast<float*>(ws + L.img1);
+    float* img2 = reinterpret_cast<float*>(ws + L.img2);
+    float* nrm1 = reinterpret_cast<float*>(ws + L.nrm1);
+    float* nrm2 = reinterpret_cast<float*>(ws + L.nrm2);
+    unsigned long long* rowkey = reinterpret_cast<unsigned long long*>(ws + L.rowkey);
+    unsigned long long* colkey = reinterpret_cast<unsigned long long*>(ws + L.colkey);
+
+    match_prep_kernel<<<dim3(L.n1p / kPrepRows, P), 1024, 0, st>>>(desc1, C, n1, L.n1p, L.Cp, point_major, img1, nrm1, rowkey);
+    RI_LAUNCH_CHECK();
+    match_prep_kernel<<<dim3(L.n2p / kPrepRows, P), 1024, 0, st>>>(desc2, C, n2, L.n2p, L.Cp, point_major, img2, nrm2, colkey);
+    RI_LAUNCH_CHECK();
+
+    const size_t smem = (size_t)kStages * kStageBytes + sizeof(GemmSmem) + 1024;
+    cudaError_t e = cudaFuncSetAttribute(match_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    match_gemm_kernel<<<dim3(L.n2p / kTileN, (n1 + kTileM - 1) / kTileM, P), kGemmThreads, smem, st>>>(
+        img1, img2, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp, rowkey, colkey);
+    RI_LAUNCH_CHECK();
+
+    match_finish_kernel<<<P, kFinThreads, 0, st>>>(desc1, desc2, C, n1, n2, L.n1p, L.n2p, point_major, nrm1, nrm2,
+                                                   rowkey, colkey, corr12, corr21, dist12, idx1, idx2, count);
+    RI_LAUNCH_CHECK();
+    return RI_OK;
+}
