@@ -46,6 +46,13 @@ int ri_knn_f32(const float* xyz1, const float* xyz2, int B, int c, int n, int m,
 int ri_knn_bilateral_f32(const float* xyz1, const float* xyz2, int B, int c, int n, int m, int k,
                          float* dist1, float* dist2, int* idx1, int* idx2, void* stream);
 
+/* The same search for scan-sized clouds (~50k points, c == 3): uniform hash grid + ring expansion instead of the full
+ * scan, results bit-identical to ri_knn_f32 (same distance expression, candidates ordered by (distance, index)).
+ * k <= 32.  workspace >= ri_knn_grid_workspace_bytes(B, n, m) bytes, 16-byte aligned. */
+size_t ri_knn_grid_workspace_bytes(int B, int n, int m);
+int ri_knn_grid_f32(const float* xyz1, const float* xyz2, int B, int n, int m, int k,
+                    float* dist1, int* idx1, void* workspace, size_t workspace_bytes, void* stream);
+
 /* knn_backward_cuda (knn/knn.cpp:27-52 -> KnnGradKernel knn/knn.cu:52-78), both directions.
  * gradxyz1 [B,c,n] and gradxyz2 [B,c,m] are overwritten. */
 int ri_knn_backward_f32(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,

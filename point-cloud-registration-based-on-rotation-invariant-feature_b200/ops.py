@@ -49,6 +49,20 @@ def _workspace(device, nbytes):
 
 
 # ---------------------------------------------------------------------------------------------- KNN
+GRID_KNN_MIN_REFS = 4096     # at and above this many reference points (c == 3, k <= 32) the hash-grid search is used
+
+
+def _knn_dir(q, r, B, c, n, m, k, d, i, dev):
+    """One direction of the k-NN: brute force for small clouds, uniform hash grid for scan-sized ones.  Both produce
+    the same bits (csrc/knn_grid.cu); this is an algorithm choice by problem size, not a backend switch."""
+    if c == 3 and k <= 32 and m >= GRID_KNN_MIN_REFS:
+        nws = _L.ri_knn_grid_workspace_bytes(B, n, m)
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        _check(_L.ri_knn_grid_f32(q.data_ptr(), r.data_ptr(), B, n, m, k, d.data_ptr(), i.data_ptr(),
+                                  ws.data_ptr(), nws, _stream()), "ri_knn_grid")
+    else:
+        _check(_L.ri_knn_f32(q.data_ptr(), r.data_ptr(), B, c, n, m, k, d.data_ptr(), i.data_ptr(), _stream()), "ri_knn")
+
 @torch.library.custom_op("ri::knn", mutates_args=())
 def knn(xyz1: torch.Tensor, xyz2: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     _req(xyz1, "xyz1", torch.float32); _req(xyz2, "xyz2", torch.float32)
@@ -60,8 +74,12 @@ def knn(xyz1: torch.Tensor, xyz2: torch.Tensor, k: int) -> tuple[torch.Tensor, t
         d2 = torch.empty((B, k, m), dtype=torch.float32, device=dev)
         i1 = torch.empty((B, k, n), dtype=torch.int32, device=dev)
         i2 = torch.empty((B, k, m), dtype=torch.int32, device=dev)
-        _check(_L.ri_knn_bilateral_f32(xyz1.data_ptr(), xyz2.data_ptr(), B, c, n, m, k,
-                                       d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(), _stream()), "ri_knn")
+        if c == 3 and k <= 32 and max(n, m) >= GRID_KNN_MIN_REFS:
+            _knn_dir(xyz1, xyz2, B, c, n, m, k, d1, i1, dev)
+            _knn_dir(xyz2, xyz1, B, c, m, n, k, d2, i2, dev)
+        else:
+            _check(_L.ri_knn_bilateral_f32(xyz1.data_ptr(), xyz2.data_ptr(), B, c, n, m, k,
+                                           d1.data_ptr(), d2.data_ptr(), i1.data_ptr(), i2.data_ptr(), _stream()), "ri_knn")
     return d1, d2, i1, i2
 
 
@@ -83,8 +101,33 @@ def knn_one(xyz1: torch.Tensor, xyz2: torch.Tensor, k: int) -> tuple[torch.Tenso
     with torch.cuda.device(dev):
         d1 = torch.empty((B, k, n), dtype=torch.float32, device=dev)
         i1 = torch.empty((B, k, n), dtype=torch.int32, device=dev)
-        _check(_L.ri_knn_f32(xyz1.data_ptr(), xyz2.data_ptr(), B, c, n, m, k, d1.data_ptr(), i1.data_ptr(), _stream()), "ri_knn")
+        _knn_dir(xyz1, xyz2, B, c, n, m, k, d1, i1, dev)
     return d1, i1
+
+
+@torch.library.custom_op("ri::knn_grid", mutates_args=())
+def knn_grid(xyz1: torch.Tensor, xyz2: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """One direction through the hash grid regardless of size (c == 3, k <= 32)."""
+    _req(xyz1, "xyz1", torch.float32); _req(xyz2, "xyz2", torch.float32)
+    dev = _same_device(xyz1, xyz2)
+    B, c, n = xyz1.shape
+    m = xyz2.shape[2]
+    if c != 3 or xyz2.shape[1] != 3:
+        raise RuntimeError("knn_grid needs 3-channel coordinates")
+    with torch.cuda.device(dev):
+        d1 = torch.empty((B, k, n), dtype=torch.float32, device=dev)
+        i1 = torch.empty((B, k, n), dtype=torch.int32, device=dev)
+        nws = _L.ri_knn_grid_workspace_bytes(B, n, m)
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        _check(_L.ri_knn_grid_f32(xyz1.data_ptr(), xyz2.data_ptr(), B, n, m, k, d1.data_ptr(), i1.data_ptr(),
+                                  ws.data_ptr(), nws, _stream()), "ri_knn_grid")
+    return d1, i1
+
+
+@knn_grid.register_fake
+def _(xyz1, xyz2, k):
+    B, c, n = xyz1.shape
+    return xyz1.new_empty((B, k, n)), xyz1.new_empty((B, k, n), dtype=torch.int32)
 
 
 @knn_one.register_fake
