@@ -34,6 +34,9 @@ extern "C" {
 /* ABI version of this header/library pair. */
 int ri_abi_version(void);
 
+/* Debug aid: a one-thread kernel that stores the device's nanosecond timer (%globaltimer) into *slot. */
+int ri_debug_stamp(unsigned long long* slot, void* stream);
+
 /* ---- k-nearest neighbours -------------------------------------------------------------------------------
  * One direction of knn_forward_cuda (knn/knn.cpp:6-25 -> KnnKernel knn/knn.cu:5-49): for each of the n points of
  * xyz1 [B,c,n] its k nearest (squared L2) among the m points of xyz2 [B,c,m].
@@ -83,13 +86,26 @@ int ri_vox_prologue_f32(const float* points, int pstride, const float* mean, int
                         int shape, float eps, int norm_mode,
                         float* xyz, float* normals, float* norm_coords, int* vox_coords, void* stream);
 
+/* Fused self-query k-NN + PPF: ri_knn_f32(xyz, xyz) followed by ri_ppf_gather_f32, in one kernel and bit-identical to
+ * that pair.  xyz / normals address [3,N] planes per cloud, cloud b at base + b * cloud_stride floats: 3N for two
+ * contiguous [B,3,N] arrays, 6N (with normals = xyz + 3N) for the interleaved [B,6,N] input batch the models receive.
+ * dist / idx [B,k,N] may both be null; ppf [B,4,k,N].  N <= 2048 and k <= 32, else RI_ERR_UNSUPPORTED. */
+int ri_knn_ppf_f32(const float* xyz, const float* normals, long long cloud_stride, int B, int N, int k,
+                   float* dist, int* idx, float* ppf, void* stream);
+
+/* De-interleave points [B,6,N] (xyz | normal) into contiguous xyz [B,3,N] and normals [B,3,N]: the `.contiguous()`
+ * copies of inputs[:, :3, :] / inputs[:, 3:, :] the reference's wrappers make (functional/knn.py:11-12,
+ * functional/ppf.py:16-19), as one launch. */
+int ri_split_xyz_normals_f32(const float* points, int B, int N, float* xyz, float* normals, void* stream);
+
 /* ---- voxelization ---------------------------------------------------------------------------------------
  * spherical_avg_voxelize_forward (spherical_voxelization/spherical_vox.cpp:17-46) and avg_voxelize_forward
  * (voxelization/vox.cpp:17-43).  feat [B,C,N]; coords [B,3,N] (fp32 normalised Cartesian for the spherical
  * variant, int32 voxel coordinates for the cube variant) -> out [B,C,r^3], ind [B,N] (-1 = undefined point),
  * cnt [B,r^3].  All three outputs are fully overwritten (no pre-zeroing needed).
- * workspace >= ri_voxelize_workspace_bytes(B, N, r) bytes of device memory, 16-byte aligned. */
-size_t ri_voxelize_workspace_bytes(int B, int N, int r);
+ * workspace >= ri_voxelize_workspace_bytes(B, C, N, r) bytes of device memory, 16-byte aligned (per-cloud cell tables
+ * plus the compact table of cell means [B][C][<=N]). */
+size_t ri_voxelize_workspace_bytes(int B, int C, int N, int r);
 int ri_sph_voxelize_f32(const float* feat, const float* coords, int B, int C, int N, int r,
                         float* out, int* ind, int* cnt, void* workspace, size_t workspace_bytes, void* stream);
 int ri_cube_voxelize_f32(const float* feat, const int* coords, int B, int C, int N, int r,
@@ -105,6 +121,32 @@ int ri_sph_voxelize_edge_f32(const float* feat, const float* coords, int B, int 
 int ri_cube_voxelize_edge_f32(const float* feat, const int* coords, int B, int C, int N, int r,
                               float* out, int* ind, int* cnt, float* edge,
                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* Phase-by-phase form of the voxelizers, for schedules that overlap or pipeline the phases (the one-shot calls above run
+ * the same three kernels back to back):
+ *   prepare  ind [B,N] and the cell tables of ALL B clouds (one launch over the batch);
+ *   means    the compact table of cell means of the clouds [b0, b1) and, when edge [B,2C,N] is non-null, their DGCNN edge
+ *            features cat(feat - mean of own cell, feat) (pvconv.py:68-90);
+ *   fill     out [B,C,r^3] / cnt [B,r^3] of the clouds [b0, b1) from the tables and means in the workspace.
+ * out, cnt, edge are the whole-batch arrays; same workspace as the one-shot calls.  Returns RI_ERR_UNSUPPORTED when the
+ * shape is outside the tiled path (N > 4096, r^3 % 4 != 0, outputs not 16-byte aligned): use the one-shot calls then. */
+int ri_sph_voxelize_prepare_f32(const float* coords, int B, int C, int N, int r, int* ind,
+                                void* workspace, size_t workspace_bytes, void* stream);
+int ri_cube_voxelize_prepare_f32(const int* coords, int B, int C, int N, int r, int* ind,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+int ri_voxelize_means_f32(const float* feat, int B, int C, int N, int r, int b0, int b1, float* edge,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int ri_voxelize_fill_f32(int B, int C, int N, int r, int b0, int b1, float* out, int* cnt,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* The prefix of the voxel branch in one launch: ri_vox_prologue_f32 + ri_*_voxelize_prepare_f32 + ri_voxelize_means_f32
+ * for all B clouds (bit-identical outputs); ri_voxelize_fill_f32 then completes the voxelization.  Arguments as
+ * ri_vox_prologue_f32 plus feat [B,C,N]; outputs norm_coords [B,3,N], vox_coords [B,3,N] (cube shapes), ind [B,N],
+ * edge [B,2C,N] (nullable) and the workspace tables.  N <= 1024 and the tiled-path conditions, else RI_ERR_UNSUPPORTED. */
+int ri_vox_front_f32(const float* points, int pstride, const float* mean, const float* feat,
+                     int B, int C, int N, int r, int shape, float eps, int norm_mode,
+                     float* norm_coords, int* vox_coords, int* ind, float* edge,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* avg_voxelize_backward == spherical_avg_voxelize_backward (vox.cpp:54-78, vox.cu:87-111):
  * grad_x [B,C,N] = grad_y[b,c,ind] / cnt (0 for undefined points); grad_x fully overwritten. */

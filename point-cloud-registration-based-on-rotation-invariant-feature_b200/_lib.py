@@ -13,6 +13,7 @@ _Z = ctypes.c_size_t
 # name -> (restype, argtypes); mirrors include/ri_b200.h one to one
 SIGNATURES = {
     "ri_abi_version": (_I, []),
+    "ri_debug_stamp": (_I, [_P, _P]),
     "ri_knn_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ri_knn_bilateral_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "ri_knn_grid_workspace_bytes": (_Z, [_I, _I, _I]),
@@ -20,12 +21,19 @@ SIGNATURES = {
     "ri_knn_backward_f32": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ri_ppf_f32": (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
     "ri_ppf_gather_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "ri_knn_ppf_f32": (_I, [_P, _P, ctypes.c_longlong, _I, _I, _I, _P, _P, _P, _P]),
     "ri_vox_prologue_f32": (_I, [_P, _I, _P, _I, _I, _I, _I, ctypes.c_float, _I, _P, _P, _P, _P, _P]),
-    "ri_voxelize_workspace_bytes": (_Z, [_I, _I, _I]),
+    "ri_split_xyz_normals_f32": (_I, [_P, _I, _I, _P, _P, _P]),
+    "ri_voxelize_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "ri_sph_voxelize_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
     "ri_cube_voxelize_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
     "ri_sph_voxelize_edge_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "ri_cube_voxelize_edge_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    "ri_sph_voxelize_prepare_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _Z, _P]),
+    "ri_cube_voxelize_prepare_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _Z, _P]),
+    "ri_voxelize_means_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),
+    "ri_voxelize_fill_f32": (_I, [_I, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
+    "ri_vox_front_f32": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _I, ctypes.c_float, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "ri_voxelize_backward_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "ri_trilinear_devox_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "ri_sph_trilinear_devox_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),

@@ -16,6 +16,7 @@
 //     divergence), and only the survivors are re-evaluated and inserted with a fully unrolled,
 //     predicated shift — ~k*(1+ln(m/k)) insertions per query instead of m.
 #include "ri_common.cuh"
+#include "ppf_math.cuh"
 
 namespace {
 
@@ -111,6 +112,77 @@ knn3_kernel(const float* __restrict__ queries, const float* __restrict__ refs, i
     }
 }
 
+// Fused self-query k-NN + point-pair features.  Same search as knn3_kernel (queries == references, whole cloud staged
+// in shared memory), and since the thread that owns a query ends up holding its k neighbours in registers, it evaluates
+// the PPF columns (centre = the query, point = each neighbour; ppf_math.cuh) right there: the neighbour's coordinates are
+// already in shared memory, its normal is staged next to them, and the [B,k,N] index tensor is never re-read.  Equals
+// ri_knn_f32(xyz, xyz) followed by ri_ppf_gather_f32 bit for bit.
+template <int KCAP>
+__global__ void __launch_bounds__(kQueriesPerCta)
+knn3_ppf_kernel(const float* __restrict__ xyz, const float* __restrict__ normals, long long cloud_stride, int n, int k,
+                float* __restrict__ dist, int* __restrict__ idx, float* __restrict__ ppf)
+{
+    extern __shared__ float4 sref[];                 // [n] (x, y, z, nx) then [n] (ny, nz, -, -)
+    float4* snrm = sref + n;
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * kQueriesPerCta + threadIdx.x;
+    const bool live = i < n;
+    const float* X = xyz + (size_t)b * cloud_stride;
+    const float* Nn = normals + (size_t)b * cloud_stride;
+    const size_t n2 = 2 * (size_t)n;
+    for (int t = threadIdx.x; t < n; t += kQueriesPerCta) {
+        sref[t] = make_float4(X[t], X[t + n], X[t + n2], Nn[t]);
+        snrm[t] = make_float4(Nn[t + n], Nn[t + n2], 0.f, 0.f);
+    }
+    __syncthreads();
+    const int iq = live ? i : n - 1;
+    const float4 me = sref[iq];
+    const float qx = me.x, qy = me.y, qz = me.z;
+
+    TopK<KCAP> top;
+    top.init();
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        const int lim = min(32, n - c0);
+        const float thr = top.worst();
+        unsigned mask = 0u;
+        if (lim == 32) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u)
+                mask |= (sqdist3(qx, qy, qz, sref[c0 + u]) < thr) ? (1u << u) : 0u;
+        } else {
+            for (int u = 0; u < lim; ++u)
+                mask |= (sqdist3(qx, qy, qz, sref[c0 + u]) < thr) ? (1u << u) : 0u;
+        }
+        while (mask) {                          // ascending reference index: keeps the stable order
+            const int u = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float d = sqdist3(qx, qy, qz, sref[c0 + u]);
+            if (d < top.worst()) top.insert(d, c0 + u);
+        }
+    }
+    if (!live) return;
+    const size_t kn = (size_t)k * n;
+    if (dist != nullptr) {
+        float* od = dist + (size_t)b * kn + i;
+        int* oi = idx + (size_t)b * kn + i;
+#pragma unroll
+        for (int s = 0; s < KCAP; ++s)
+            if (s < k) { od[(size_t)s * n] = top.d[s]; oi[(size_t)s * n] = top.j[s]; }
+    }
+    const float4 mn = snrm[i];
+    float* O = ppf + (size_t)b * 4 * kn + i;
+#pragma unroll
+    for (int s = 0; s < KCAP; ++s) {
+        if (s < k) {
+            const int j = top.j[s];              // an unfilled slot holds index 0, exactly what the two-kernel path gathers
+            const float4 p = sref[j], pq = snrm[j];
+            const Ppf4 r = ppf_column(me.x, me.y, me.z, me.w, mn.x, mn.y, p.x, p.y, p.z, p.w, pq.x, pq.y);
+            float* o = O + (size_t)s * n;
+            o[0] = r.a1; o[kn] = r.a2; o[2 * kn] = r.a3; o[3 * kn] = r.dn;
+        }
+    }
+}
+
 // Generic path: any channel count c, any k.  Thread per query, list kept in the output arrays
 // (coalesced along the query index).  Correct for everything; used only off the hot configuration.
 __global__ void __launch_bounds__(kQueriesPerCta)
@@ -152,6 +224,12 @@ int launch_knn(const float* queries, const float* refs, int B, int c, int n, int
     if (B == 0 || n == 0) return RI_OK;
     dim3 grid((n + kQueriesPerCta - 1) / kQueriesPerCta, B);
     const size_t smem = (size_t)(m < kRefTile ? (m > 0 ? m : 1) : kRefTile) * sizeof(float4);
+    static bool carveout_set = false;
+    if (!carveout_set) {
+        ri_prefer_step_carveout(knn3_kernel<8>); ri_prefer_step_carveout(knn3_kernel<16>);
+        ri_prefer_step_carveout(knn3_kernel<20>); ri_prefer_step_carveout(knn3_kernel<32>);
+        carveout_set = true;
+    }
     if (c == 3 && k <= 32) {
         if (k <= 8) knn3_kernel<8><<<grid, kQueriesPerCta, smem, st>>>(queries, refs, n, m, k, dist, idx);
         else if (k <= 16) knn3_kernel<16><<<grid, kQueriesPerCta, smem, st>>>(queries, refs, n, m, k, dist, idx);
@@ -181,4 +259,35 @@ extern "C" int ri_knn_bilateral_f32(const float* xyz1, const float* xyz2, int B,
     int rc = ri_knn_f32(xyz1, xyz2, B, c, n, m, k, dist1, idx1, stream);
     if (rc != RI_OK) return rc;
     return ri_knn_f32(xyz2, xyz1, B, c, m, n, k, dist2, idx2, stream);
+}
+
+// Fused self-query k-NN + PPF (see knn3_ppf_kernel).  xyz / normals address [3,N] planes per cloud, cloud b at
+// base + b * cloud_stride floats (3N for two contiguous [B,3,N] arrays; 6N with normals = xyz + 3N for the interleaved
+// [B,6,N] input batch).  dist / idx may both be null when only the features are wanted.
+extern "C" int ri_knn_ppf_f32(const float* xyz, const float* normals, long long cloud_stride, int B, int N, int k,
+                              float* dist, int* idx, float* ppf, void* stream)
+{
+    if (B < 0 || N < 0 || k <= 0 || cloud_stride < 0 || ppf == nullptr || ((dist == nullptr) != (idx == nullptr)))
+        return RI_ERR_BAD_ARG;
+    if (k > 32 || N > kRefTile || B > 65535) return RI_ERR_UNSUPPORTED;
+    if (B == 0 || N == 0) return RI_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)N * 2 * sizeof(float4);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(knn3_ppf_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kRefTile * sizeof(float4)));
+        cudaFuncSetAttribute(knn3_ppf_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kRefTile * sizeof(float4)));
+        cudaFuncSetAttribute(knn3_ppf_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kRefTile * sizeof(float4)));
+        cudaFuncSetAttribute(knn3_ppf_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kRefTile * sizeof(float4)));
+        ri_prefer_step_carveout(knn3_ppf_kernel<8>); ri_prefer_step_carveout(knn3_ppf_kernel<16>);
+        ri_prefer_step_carveout(knn3_ppf_kernel<20>); ri_prefer_step_carveout(knn3_ppf_kernel<32>);
+        attr_set = true;
+    }
+    dim3 grid((N + kQueriesPerCta - 1) / kQueriesPerCta, B);
+    if (k <= 8) knn3_ppf_kernel<8><<<grid, kQueriesPerCta, smem, st>>>(xyz, normals, cloud_stride, N, k, dist, idx, ppf);
+    else if (k <= 16) knn3_ppf_kernel<16><<<grid, kQueriesPerCta, smem, st>>>(xyz, normals, cloud_stride, N, k, dist, idx, ppf);
+    else if (k <= 20) knn3_ppf_kernel<20><<<grid, kQueriesPerCta, smem, st>>>(xyz, normals, cloud_stride, N, k, dist, idx, ppf);
+    else knn3_ppf_kernel<32><<<grid, kQueriesPerCta, smem, st>>>(xyz, normals, cloud_stride, N, k, dist, idx, ppf);
+    RI_LAUNCH_CHECK();
+    return RI_OK;
 }

@@ -13,35 +13,9 @@
 // One CTA per cloud; input is the interleaved [B,6,N] (xyz | normal) batch, outputs are the contiguous planes the
 // other kernels take: xyz [B,3,N], normals [B,3,N], norm_coords [B,3,N] and, for the cube variant, int voxel coords.
 #include "ri_common.cuh"
+#include "prologue_math.cuh"
 
 namespace {
-
-constexpr int kProThreads = 512;
-
-__device__ __forceinline__ float radius3(float x, float y, float z, int mode)
-{
-    float q;
-    switch (mode) {
-        case 0: q = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x))); break;
-        case 1: q = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)); break;
-        case 2: q = __fadd_rn(__fmul_rn(x, x), __fadd_rn(__fmul_rn(y, y), __fmul_rn(z, z))); break;
-        case 3: q = __fmaf_rn(z, z, __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))); break;
-        default: q = __fmaf_rn(x, x, __fmaf_rn(y, y, __fmul_rn(z, z))); break;
-    }
-    return __fsqrt_rn(q);
-}
-
-__device__ __forceinline__ float block_max(float v, float* sred)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float m = sred[0];
-    for (int w = 1; w < kProThreads / 32; ++w) m = fmaxf(m, sred[w]);
-    __syncthreads();
-    return m;
-}
 
 // shape: 0 = cube, normalize=False   ((x - mean + 1) / 2 * r, clamp, round)
 //        1 = cube, normalize=True    ((x - mean) / (2 * maxradius + eps) + 0.5, * r, clamp, round)
@@ -103,8 +77,61 @@ extern "C" int ri_vox_prologue_f32(const float* points, int pstride, const float
     if (B < 0 || N < 0 || r <= 0 || (pstride != 3 && pstride != 6) || shape < 0 || shape > 2) return RI_ERR_BAD_ARG;
     if (norm_coords == nullptr || (shape != 2 && vox_coords == nullptr)) return RI_ERR_BAD_ARG;
     if (B == 0 || N == 0) return RI_OK;
+    static bool carveout_set = false;
+    if (!carveout_set) { ri_prefer_step_carveout(prologue_kernel); carveout_set = true; }
     prologue_kernel<<<B, kProThreads, 0, (cudaStream_t)stream>>>(points, pstride, mean, N, r, shape, eps, norm_mode,
                                                                  xyz, normals, norm_coords, vox_coords);
+    RI_LAUNCH_CHECK();
+    return RI_OK;
+}
+
+// De-interleave a [B, 6, N] (xyz | normal) batch into the contiguous xyz [B,3,N] and normals [B,3,N] planes the k-NN and
+// PPF kernels take — the `.contiguous()` copies of the slices inputs[:, :3, :] / inputs[:, 3:, :] that the reference's
+// wrappers make (functional/knn.py:11-12, functional/ppf.py:16-19), as one launch.
+namespace {
+__global__ void __launch_bounds__(256)
+split6_kernel(const float4* __restrict__ points, size_t quads_per_half, float4* __restrict__ xyz, float4* __restrict__ normals)
+{
+    // per cloud the first 3N floats are xyz, the next 3N the normals: a straight vectorised copy
+    const size_t b = blockIdx.y;
+    const float4* P = points + b * 2 * quads_per_half;
+    for (size_t i = blockIdx.x * 256 + threadIdx.x; i < quads_per_half; i += (size_t)gridDim.x * 256) {
+        xyz[b * quads_per_half + i] = P[i];
+        normals[b * quads_per_half + i] = P[quads_per_half + i];
+    }
+}
+__global__ void __launch_bounds__(256)
+split6_scalar_kernel(const float* __restrict__ points, size_t half, float* __restrict__ xyz, float* __restrict__ normals)
+{
+    const size_t b = blockIdx.y;
+    const float* P = points + b * 2 * half;
+    for (size_t i = blockIdx.x * 256 + threadIdx.x; i < half; i += (size_t)gridDim.x * 256) {
+        xyz[b * half + i] = P[i];
+        normals[b * half + i] = P[half + i];
+    }
+}
+}  // namespace
+
+extern "C" int ri_split_xyz_normals_f32(const float* points, int B, int N, float* xyz, float* normals, void* stream)
+{
+    if (B < 0 || N < 0 || B > 65535) return RI_ERR_BAD_ARG;
+    if (B == 0 || N == 0) return RI_OK;
+    static bool carveout_set = false;
+    if (!carveout_set) {
+        ri_prefer_step_carveout(split6_kernel); ri_prefer_step_carveout(split6_scalar_kernel);
+        carveout_set = true;
+    }
+    const size_t half = (size_t)3 * N;
+    const bool vec = (half % 4 == 0) && (((uintptr_t)points | (uintptr_t)xyz | (uintptr_t)normals) % 16 == 0);
+    if (vec) {
+        const size_t quads = half / 4;
+        dim3 grid((unsigned)((quads + 255) / 256 > 8 ? 8 : (quads + 255) / 256), B);
+        split6_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(points), quads,
+                                                              reinterpret_cast<float4*>(xyz), reinterpret_cast<float4*>(normals));
+    } else {
+        dim3 grid((unsigned)((half + 255) / 256 > 8 ? 8 : (half + 255) / 256), B);
+        split6_scalar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, half, xyz, normals);
+    }
     RI_LAUNCH_CHECK();
     return RI_OK;
 }

@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define RI_OK 0
 #define RI_ERR_BAD_ARG (-1)
@@ -37,6 +38,29 @@ static inline int ri_num_sms()
         cached = n;
     }
     return cached;
+}
+
+// L1 / shared-memory split of the kernels that are meant to run NEXT TO the grid writer (vox_fill: a 96 KB ring per SM).
+// An SM cannot host CTAs of kernels configured for different carveouts at the same time — it drains first — which
+// silently serialises branches that were meant to overlap (measured on a B200: k-NN next to the grid writer 154 us with
+// mismatched carveouts, 108 us matched; k-NN next to the devoxelizer 285 us against 78 + 54 us one after the other).
+// So the k-NN / PPF branch and the prefix of the voxel branch all ask for the writer's max-shared split.  The
+// devoxelizer must NOT: its gathers use L1 as their miss buffer and its speed follows the L1 size (54 us with the
+// default max-L1 split, 73 / 88 / 118 / 231 us with 100 / 132 / 164 / 228 KB of shared memory), so it keeps the default
+// and is scheduled after the max-shared kernels have left the SMs.
+static inline int ri_step_carveout_percent()
+{
+    static int pct = 0;
+    if (pct == 0) {
+        pct = 100;
+        if (const char* ev = getenv("RI_CARVEOUT_PCT")) { const int v = atoi(ev); if (v >= 1 && v <= 100) pct = v; }
+    }
+    return pct;
+}
+template <typename K>
+static inline void ri_prefer_step_carveout(K kernel)
+{
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, ri_step_carveout_percent());
 }
 
 // x*x' + y*y' + z*z' as nvcc contracts it for the reference: fma(z,z', fma(x,x', y*y')).

@@ -17,17 +17,22 @@
 //   K1  vox_prepare   one CTA per cloud: bin every point (bit-exact), sort (cell,point) keys with a shared-
 //                     memory bitonic network, emit the compact occupied-cell table of the cloud
 //                     (cell id, first point, point count) and, per tile of the grid, where its cells start.
-//   K2  vox_fill      persistent CTAs (2 per SM).  A work item is (cloud, grid tile, group of channel planes).
+//   K2  vox_means     grid (8-channel groups, clouds): the mean of every occupied cell in every channel, one
+//                     thread per cell, points summed in ascending order; written as a compact table
+//                     means[b][c][cell slot] (coalesced).  The same CTA then emits the DGCNN edge features
+//                     edge[b] = cat(feat - mean_of_own_cell, feat) point by point (fully coalesced) when asked to.
+//   K3  vox_fill      persistent CTAs (2 per SM).  A work item is (cloud, grid tile, group of channel planes).
 //                     Each CTA keeps a ring of zeroed 32 KB tiles in shared memory; per plane it patches the
-//                     few occupied cells of the tile with their means (one thread per cell, sequential sum),
-//                     and ships the tile to HBM with ONE bulk async copy (cp.async.bulk shared->global, the
-//                     TMA engine, SASS UBLKCP), overlapping the next plane's patching with the store.  The
-//                     integer count grid goes out the same way as plane C.  Nothing is memset, nothing is
-//                     read back, `out` is written exactly once, and there are no atomics at all.
+//                     few occupied cells of the tile with their means (coalesced reads of the compact table,
+//                     8 planes prefetched at a time) and ships the tile to HBM with ONE bulk async copy
+//                     (cp.async.bulk shared->global, the TMA engine, SASS UBLKCP), overlapping the next plane's
+//                     patching with the store.  The integer count grid goes out the same way as plane C.
+//                     Nothing is memset, nothing is read back, `out` is written exactly once, no atomics at all.
 //
 //   Fallback (N > 4096 points per cloud, r^3 not a multiple of 4, or misaligned pointers): memset + integer
 //   atomics for counts + float atomics for the means over a (point tile, channel group, cloud) grid.
 #include "ri_common.cuh"
+#include "prologue_math.cuh"
 #include <stdlib.h>
 
 extern "C" int ri_voxel_edge_gather_f32(const float* avg, const float* feat, const int* inds, int B, int C, int N, int s,
@@ -38,15 +43,18 @@ namespace {
 constexpr int kPrepThreads = 512;
 constexpr int kSmallCloudMax = 4096;     // K1 sorts a whole cloud inside one CTA
 constexpr int kTileCells = 8192;         // 32 KB of fp32 per tile
-constexpr int kRing = 3;                 // tiles in flight per CTA
+constexpr int kRing = 3;                 // default number of 32 KB tiles in a CTA's ring
 constexpr int kFillThreads = 256;
-constexpr int kPlaneBatch = 8;            // channel planes whose gathers are issued together
-constexpr int kFillMaxRegs = 96;          // 2 CTAs/SM use 48K registers: leaves room for the k-NN CTAs of the other branch
+constexpr int kFillCtasPerSm = 1;         // one 96 KB ring per SM keeps the bulk-store engine fed (measured: same speed as two)
+constexpr int kMaxFillCalls = 64;        // distinct cloud ranges one workspace can serve between two prepares
+constexpr int kPlaneBatch = 4;            // channel planes whose table reads are issued together
+constexpr int kPlaneGroup = 8;            // planes per work item (>= kRing)
+constexpr int kFillMaxRegs = 80;          // a small footprint: the k-NN / PPF CTAs of the other branch share the SM
 constexpr int kSegCache = 2;             // occupied cells per thread whose table entries live in registers
 constexpr unsigned kNoCell = 0xffffffffu;
 
 struct VoxWs {                            // per-cloud int32 workspace layout
-    int stride, off_pid, off_cell, off_start, off_tile, off_meta;
+    int stride, off_pid, off_cell, off_start, off_tile, off_meta, off_segof;
 };
 __host__ __device__ inline VoxWs vox_ws_layout(int N, int ntiles)
 {
@@ -56,7 +64,8 @@ __host__ __device__ inline VoxWs vox_ws_layout(int N, int ntiles)
     w.off_start = 2 * N;
     w.off_tile = 3 * N + 1;
     w.off_meta = w.off_tile + ntiles + 1;
-    w.stride = (w.off_meta + 2 + 3) / 4 * 4;
+    w.off_segof = w.off_meta + 2;            // table slot of every point (-1: outside the grid)
+    w.stride = (w.off_segof + N + 3) / 4 * 4;
     return w;
 }
 
@@ -172,6 +181,9 @@ vox_prepare_kernel(const void* __restrict__ coords_v, int N, int P, int r, int s
                     scell[seg] = (int)cell;
                     ++seg;
                 }
+                W[L.off_segof + (int)(unsigned)(key & 0xffffffffu)] = seg - 1;
+            } else if (u < N) {
+                W[L.off_segof + (int)(unsigned)(key & 0xffffffffu)] = -1;
             }
         }
     }
@@ -190,67 +202,343 @@ vox_prepare_kernel(const void* __restrict__ coords_v, int N, int P, int r, int s
 }
 
 // ------------------------------------------------------------------------------------------------ K2
-// One occupied cell ("segment" of the cell-sorted point list) of the current tile, as cached by its thread.
-struct SegRegs { int off, st, cnt; };
+// means[b][c][slot] = sum over the cell's points (ascending point order) of feat[b][c][i] * (1.0f / count)
+// (vox.cu:66-70 / spherical_vox.cu:112-116 form the same products; the reference adds them in atomic arrival order).
+// With `edge` != null the CTA then writes the DGCNN edge features of its channels (pvconv.py:68-90):
+//   edge[b, c, i] = feat - mean of i's cell (0 for a point outside the grid),  edge[b, C + c, i] = feat.
+constexpr int kMeanChans = 8;
+constexpr int kMeanThreads = 256;
 
-// Mean of channel plane p over one segment (ascending point order), or the count itself for plane C.
-// When `edge` is given also emits the DGCNN edge features of the segment's points:
-//   edge[b, p, i] = feat - mean,  edge[b, C+p, i] = feat      (pvconv.py:68-90; undefined points: see below)
-__device__ __forceinline__ float seg_value(const SegRegs sg, int p, int C, int N, const float* __restrict__ Fp,
-                                           const int* __restrict__ pid, float* __restrict__ edge_rel,
-                                           float* __restrict__ edge_cpy)
+__global__ void __launch_bounds__(kMeanThreads)
+vox_means_kernel(const float* __restrict__ feat, const int* __restrict__ ws, int b0, int C, int N, int ntiles, int ucap,
+                 int smem_means, float* __restrict__ means, float* __restrict__ edge)
 {
-    if (p >= C) return __int_as_float(sg.cnt);
-    const float inv = __fdiv_rn(1.0f, (float)sg.cnt);                               // vox.cu:66
-    float acc = 0.f;
-    for (int u = sg.st; u < sg.st + sg.cnt; ++u)
-        acc = __fadd_rn(acc, __fmul_rn(__ldg(Fp + __ldg(pid + u)), inv));          // vox.cu:68-70, point order
-    if (edge_rel != nullptr) {
-        for (int u = sg.st; u < sg.st + sg.cnt; ++u) {
-            const int i = __ldg(pid + u);
-            const float f = __ldg(Fp + i);
-            edge_rel[i] = __fsub_rn(f, acc);
-            edge_cpy[i] = f;
-        }
+    // The CTA's 8 feature rows are staged in shared memory (coalesced read, 32 KB at N = 1024): the per-cell gathers
+    // then never touch L1, so the kernel is indifferent to the L1/shared split and can share SMs with the k-NN branch
+    // under the grid writer's max-shared carveout.  Row stride N + 1 words spreads the 8 rows over the banks.
+    extern __shared__ float sfeat[];                   // [kMeanChans][N + 1], then the cell means [kMeanChans][U]
+    const int b = b0 + blockIdx.y, c0 = blockIdx.x * kMeanChans, tid = threadIdx.x;
+    const VoxWs L = vox_ws_layout(N, ntiles);
+    const int* W = ws + (size_t)b * L.stride;
+    const int* pid = W + L.off_pid;
+    const int U = __ldg(W + L.off_meta);
+    const int nch = min(kMeanChans, C - c0);
+    const int ld = N + 1;
+    const float* F = feat + ((size_t)b * C + c0) * N;
+    float* M = means + ((size_t)b * C + c0) * ucap;
+    float* smean = sfeat + kMeanChans * ld;
+
+    for (int e = tid; e < nch * N; e += kMeanThreads) {
+        const int j = e / N, i = e - j * N;
+        sfeat[j * ld + i] = __ldg(F + (size_t)j * N + i);
     }
-    return acc;
+    __syncthreads();
+    for (int sg = tid; sg < U; sg += kMeanThreads) {
+        const int st = __ldg(W + L.off_start + sg);
+        const int cnt = __ldg(W + L.off_start + sg + 1) - st;
+        const float inv = __fdiv_rn(1.0f, (float)cnt);                                     // vox.cu:66
+        float acc[kMeanChans];
+#pragma unroll
+        for (int j = 0; j < kMeanChans; ++j) acc[j] = 0.f;
+        for (int u = st; u < st + cnt; ++u) {                                               // ascending point order
+            const int i = __ldg(pid + u);
+#pragma unroll
+            for (int j = 0; j < kMeanChans; ++j)
+                if (j < nch) acc[j] = __fadd_rn(acc[j], __fmul_rn(sfeat[j * ld + i], inv));           // vox.cu:68-70
+        }
+#pragma unroll
+        for (int j = 0; j < kMeanChans; ++j)
+            if (j < nch) {
+                M[(size_t)j * ucap + sg] = acc[j];
+                if (smem_means) smean[j * ucap + sg] = acc[j];
+            }
+    }
+    if (edge == nullptr) return;
+    __syncthreads();
+    const int* segof = W + L.off_segof;
+    float* E = edge + ((size_t)b * 2 * C + c0) * N;
+    for (int i = tid; i < N; i += kMeanThreads) {
+        const int sg = __ldg(segof + i);
+#pragma unroll
+        for (int j = 0; j < kMeanChans; ++j)
+            if (j < nch) {
+                const float f = sfeat[j * ld + i];
+                float mu = 0.f;
+                if (sg >= 0) mu = smem_means ? smean[j * ucap + sg] : __ldcg(M + (size_t)j * ucap + sg);
+                E[(size_t)j * N + i] = sg >= 0 ? __fsub_rn(f, mu) : 0.f;
+                E[((size_t)C + j) * N + i] = f;
+            }
+    }
 }
 
-__global__ void __maxnreg__(kFillMaxRegs)
-vox_fill_kernel(const float* __restrict__ feat, const int* __restrict__ ws, int B, int C, int N, int s,
-                int tile_cells, int ntiles,
-                float* __restrict__ out, int* __restrict__ cnt, float* __restrict__ edge)
+// ------------------------------------------------------------------------------------------ K0+K1+K2 fused
+// The whole prefix of the voxel branch in ONE launch, for clouds that fit a CTA comfortably (N <= kFrontMaxN):
+// coordinate prologue (prologue.cu) + prepare (K1) + means/edge (K2).  Grid = (8-channel groups, clouds); every CTA of a
+// cloud repeats the cheap per-cloud part (normalise, bin, sort 1024 keys, build the cell table — in shared memory) and
+// then does its own channel group; the CTA of group 0 also publishes norm_coords / vox_coords / ind and the tables the
+// grid writer needs.  Three dependent, latency-bound launches (5 + 15 + 25 us, each with 32-288 CTAs) become one whose
+// feature staging (cp.async) overlaps the sort.
+constexpr int kFrontThreads = 512;
+constexpr int kFrontMaxN = 1024;
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
 {
-    extern __shared__ __align__(128) float sring[];        // kRing tiles of tile_cells floats
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(ri_smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
+template <bool SPH>
+__global__ void __launch_bounds__(kFrontThreads)
+vox_front_kernel(const float* __restrict__ points, int pstride, const float* __restrict__ mean,
+                 const float* __restrict__ feat, int C, int N, int P, int r, int s, int tile_cells, int ntiles,
+                 int shape, float eps, int norm_mode, int ucap,
+                 float* __restrict__ norm_coords, int* __restrict__ vox_coords, int* __restrict__ ind,
+                 int* __restrict__ ws, float* __restrict__ means, float* __restrict__ edge)
+{
+    extern __shared__ unsigned long long skeys[];          // [P] sort keys
+    int* scell = reinterpret_cast<int*>(skeys + P);        // [P] cell of each table slot
+    int* spid = scell + P;                                 // [N] cell-sorted point ids
+    int* sstart = spid + N;                                // [N + 1] first sorted slot of each table slot
+    int* ssegof = sstart + N + 1;                          // [N] table slot of each point (-1 outside the grid)
+    float* sfeat = reinterpret_cast<float*>(ssegof + N + ((3 * N + 1) & 1));   // [kMeanChans][N + 4], 8-byte aligned
+    const int ld = N + 4;
+    float* smean = sfeat + kMeanChans * ld;                // [kMeanChans][ucap]
+    __shared__ float sred[kFrontThreads / 32];
+    __shared__ int swarp_heads[kFrontThreads / 32];
+    __shared__ int swarp_valid[kFrontThreads / 32];
+    __shared__ int stotal[2];
+
+    const int b = blockIdx.y, g = blockIdx.x, tid = threadIdx.x;
+    const bool publish = g == 0;
+    const int c0 = g * kMeanChans;
+    const int nch = min(kMeanChans, C - c0);
+    const VoxWs L = vox_ws_layout(N, ntiles);
+    int* W = ws + (size_t)b * L.stride;
+
+    // ---- this CTA's feature rows start flowing into shared memory now; they are first needed after the sort
+    {
+        const float* F = feat + ((size_t)b * C + c0) * N;
+        for (int e = tid; e < nch * N; e += kFrontThreads) {
+            const int j = e / N, i = e - j * N;
+            cp_async4(sfeat + j * ld + i, F + (size_t)j * N + i);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
+    // ---- coordinate prologue (prologue.cu::prologue_kernel, same arithmetic)
+    const float* Pt = points + (size_t)b * pstride * N;
+    const float mx = mean[b * 3 + 0], my = mean[b * 3 + 1], mz = mean[b * 3 + 2];
+    const size_t o3 = (size_t)b * 3 * N;
+    float denom = 1.0f;
+    if (shape != 0) {
+        float m = 0.f;
+        for (int i = tid; i < N; i += kFrontThreads)
+            m = fmaxf(m, radius3(__fsub_rn(Pt[i], mx), __fsub_rn(Pt[i + N], my), __fsub_rn(Pt[i + 2 * (size_t)N], mz), norm_mode));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((tid & 31) == 0) sred[tid >> 5] = m;
+        __syncthreads();
+        m = sred[0];
+        for (int w = 1; w < kFrontThreads / 32; ++w) m = fmaxf(m, sred[w]);
+        denom = (shape == 1) ? __fadd_rn(__fmul_rn(m, 2.0f), eps) : __fadd_rn(m, 1e-20f);
+    }
+    const float rf = (float)r, hi = (float)(r - 1);
+    for (int i = tid; i < P; i += kFrontThreads) {
+        unsigned long long key = ~0ull;
+        if (i < N) {
+            float v[3]; int vi[3] = {0, 0, 0};
+            v[0] = ri_prologue_coord(__fsub_rn(Pt[i], mx), shape, denom, rf, hi, &vi[0]);
+            v[1] = ri_prologue_coord(__fsub_rn(Pt[i + N], my), shape, denom, rf, hi, &vi[1]);
+            v[2] = ri_prologue_coord(__fsub_rn(Pt[i + 2 * (size_t)N], mz), shape, denom, rf, hi, &vi[2]);
+            int cell;
+            if (SPH) cell = ri_sph_cell(v[0], v[1], v[2], r);
+            else cell = vi[0] * r * r + vi[1] * r + vi[2];                             // vox.cu:31
+            if (publish) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    norm_coords[o3 + (size_t)a * N + i] = v[a];
+                    if (!SPH) vox_coords[o3 + (size_t)a * N + i] = vi[a];
+                }
+                ind[(size_t)b * N + i] = cell;
+            }
+            const unsigned hi32 = (cell >= 0 && cell < s) ? (unsigned)cell : kNoCell;
+            key = ((unsigned long long)hi32 << 32) | (unsigned)i;
+        }
+        skeys[i] = key;
+    }
+    __syncthreads();
+
+    // ---- K1: bitonic sort of (cell, point), cell table (vox_prepare_kernel, tables kept in shared memory)
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int j = size >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (P >> 1); t += kFrontThreads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const unsigned long long a = skeys[i], c = skeys[l];
+                const bool up = (i & size) == 0;
+                if ((a > c) == up) { skeys[i] = c; skeys[l] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    const int E = (P + kFrontThreads - 1) / kFrontThreads;
+    const int u0 = tid * E;
+    int heads = 0, valid = 0;
+    for (int e = 0; e < E; ++e) {
+        const int u = u0 + e;
+        if (u < P) {
+            const unsigned long long key = skeys[u];
+            if ((unsigned)(key >> 32) != kNoCell) {
+                ++valid;
+                if (u == 0 || (unsigned)(skeys[u - 1] >> 32) != (unsigned)(key >> 32)) ++heads;
+            }
+        }
+    }
+    const int lane = tid & 31, wid = tid >> 5;
+    int incl = heads;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    int vsum = valid;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+    if (lane == 31) swarp_heads[wid] = incl;
+    if (lane == 0) swarp_valid[wid] = vsum;
+    __syncthreads();
+    if (wid == 0) {
+        int h = lane < kFrontThreads / 32 ? swarp_heads[lane] : 0;
+        int v = lane < kFrontThreads / 32 ? swarp_valid[lane] : 0;
+        int hsum = h;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, hsum, o);
+            if (lane >= o) hsum += t;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane < kFrontThreads / 32) swarp_heads[lane] = hsum - h;
+        if (lane == kFrontThreads / 32 - 1) stotal[0] = hsum;
+        if (lane == 0) stotal[1] = v;
+    }
+    __syncthreads();
+    int seg = swarp_heads[wid] + (incl - heads);
+    const int U = stotal[0], nvalid = stotal[1];
+    for (int e = 0; e < E; ++e) {
+        const int u = u0 + e;
+        if (u < P) {
+            const unsigned long long key = skeys[u];
+            const int pt = (int)(unsigned)(key & 0xffffffffu);
+            if (u < N) { spid[u] = pt; if (publish) W[L.off_pid + u] = pt; }
+            if ((unsigned)(key >> 32) != kNoCell) {
+                const unsigned cell = (unsigned)(key >> 32);
+                if (u == 0 || (unsigned)(skeys[u - 1] >> 32) != cell) {
+                    scell[seg] = (int)cell;
+                    sstart[seg] = u;
+                    if (publish) { W[L.off_cell + seg] = (int)cell; W[L.off_start + seg] = u; }
+                    ++seg;
+                }
+                ssegof[pt] = seg - 1;
+                if (publish) W[L.off_segof + pt] = seg - 1;
+            } else if (u < N) {
+                ssegof[pt] = -1;
+                if (publish) W[L.off_segof + pt] = -1;
+            }
+        }
+    }
+    if (tid == 0) {
+        sstart[U] = nvalid;
+        if (publish) { W[L.off_start + U] = nvalid; W[L.off_meta] = U; W[L.off_meta + 1] = nvalid; }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    if (publish) {
+        for (int t = tid; t <= ntiles; t += kFrontThreads) {
+            const long long want = (long long)t * tile_cells;
+            int lo = 0, hi2 = U;
+            while (lo < hi2) {
+                const int mid = (lo + hi2) >> 1;
+                if ((long long)scell[mid] < want) lo = mid + 1; else hi2 = mid;
+            }
+            W[L.off_tile + t] = lo;
+        }
+    }
+    if (nch <= 0) return;
+
+    // ---- K2: cell means of this CTA's channels (ascending point order), then the edge features
+    float* M = means + ((size_t)b * C + c0) * ucap;
+    for (int sg = tid; sg < U; sg += kFrontThreads) {
+        const int st = sstart[sg];
+        const int cnt = sstart[sg + 1] - st;
+        const float inv = __fdiv_rn(1.0f, (float)cnt);                                     // vox.cu:66
+        float acc[kMeanChans];
+#pragma unroll
+        for (int j = 0; j < kMeanChans; ++j) acc[j] = 0.f;
+        for (int u = st; u < st + cnt; ++u) {
+            const int i = spid[u];
+#pragma unroll
+            for (int j = 0; j < kMeanChans; ++j)
+                if (j < nch) acc[j] = __fadd_rn(acc[j], __fmul_rn(sfeat[j * ld + i], inv));           // vox.cu:68-70
+        }
+#pragma unroll
+        for (int j = 0; j < kMeanChans; ++j)
+            if (j < nch) { M[(size_t)j * ucap + sg] = acc[j]; smean[j * ucap + sg] = acc[j]; }
+    }
+    if (edge == nullptr) return;
+    __syncthreads();
+    float* Eo = edge + ((size_t)b * 2 * C + c0) * N;
+    for (int e = tid; e < nch * N; e += kFrontThreads) {
+        const int j = e / N, i = e - j * N;
+        const int sg = ssegof[i];
+        const float f = sfeat[j * ld + i];
+        Eo[(size_t)j * N + i] = sg >= 0 ? __fsub_rn(f, smean[j * ucap + sg]) : 0.f;
+        Eo[((size_t)C + j) * N + i] = f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+// One occupied cell ("segment" of the cell-sorted point list) of the current tile, as cached by its thread.
+struct SegRegs { int off, sg, cnt; };      // offset inside the tile, slot in the cloud's cell table, point count
+
+template <int RING>
+__global__ void __maxnreg__(kFillMaxRegs)
+vox_fill_kernel(const float* __restrict__ means, const int* __restrict__ ws, int b0, int B, int C, int N, int s,
+                int tile_cells, int ntiles, int ucap, int* __restrict__ work_counter,
+                float* __restrict__ out, int* __restrict__ cnt)
+{
+    extern __shared__ __align__(128) float sring[];        // RING tiles of tile_cells floats
+    __shared__ int s_item[2];
     const int tid = threadIdx.x;
     const VoxWs L = vox_ws_layout(N, ntiles);
     const int planes = C + 1;                              // plane C is the integer count grid
 
-    for (int i = tid; i < kRing * tile_cells / 4; i += kFillThreads)
+    // Work items = (cloud, tile, group of kPlaneGroup planes), handed out through one global counter, plane group
+    // fastest: a CTA that draws consecutive numbers usually stays on the same (cloud, tile) and keeps its cached cell
+    // table.  Dynamic hand-out instead of a static slice per CTA: when this kernel shares the SMs with the k-NN branch
+    // some of its CTAs only become resident late — they then simply take fewer items, the kernel does not wait for them.
+    const int groups = (planes + kPlaneGroup - 1) / kPlaneGroup;
+    const int total_items = B * ntiles * groups;
+    if (tid == 0) s_item[0] = atomicAdd(work_counter, 1);
+    for (int i = tid; i < RING * tile_cells / 4; i += kFillThreads)
         reinterpret_cast<float4*>(sring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
-    // Work = the flattened sequence of (cloud, tile, plane) units, 32 KB of output each.  Every CTA takes one
-    // contiguous, equally long slice of it: perfectly balanced, and a CTA changes (cloud, tile) at most
-    // ceil(slice / planes) + 1 times, so the per-item table fetch is paid once or twice per CTA, not per group.
-    const long long total = (long long)B * ntiles * planes;
-    const long long u_begin = total * blockIdx.x / gridDim.x;
-    const long long u_end = total * (blockIdx.x + 1) / gridDim.x;
     int slot = 0;
     // The ring slots are never re-zeroed wholesale.  Between two bulk copies out of a slot only the occupied cells
-    // of the tile are rewritten; when the CTA moves on to another (cloud, tile) the cells of the PREVIOUS item are
+    // of the tile are rewritten; when the CTA moves on to another (cloud, tile) the cells of the PREVIOUS tile are
     // cleared lazily, slot by slot, right before each slot's first reuse — so the copies still in flight are never
-    // waited for (no pipeline drain at an item switch).
-    SegRegs seg[kSegCache];                                 // this item's cells owned by this thread
-    int old_off[kSegCache];                                 // previous item's cells (offset, or -1)
+    // waited for (no pipeline drain at a tile switch).
+    SegRegs seg[kSegCache];                                 // this tile's cells owned by this thread
+    int old_off[kSegCache];                                 // previous tile's cells (offset, or -1)
 #pragma unroll
-    for (int q = 0; q < kSegCache; ++q) { seg[q].off = 0; seg[q].st = 0; seg[q].cnt = 0; old_off[q] = -1; }
-    int extra_lo = 0, extra_hi = 0, cur_cell_lo = 0;        // cells beyond the register cache (rare), current item
+    for (int q = 0; q < kSegCache; ++q) { seg[q].off = 0; seg[q].sg = 0; seg[q].cnt = 0; old_off[q] = -1; }
+    int extra_lo = 0, extra_hi = 0, cur_cell_lo = 0;        // cells beyond the register cache (rare), current tile
     int old_extra_lo = 0, old_extra_hi = 0, old_cell_lo = 0;
     const int* curW = nullptr;
     const int* oldW = nullptr;
-    int stale = 0;                                          // ring slots that still carry the previous item's cells
-    int prev_planes = kRing;
+    int cur_bt = -1;
+    int stale = 0;                                          // ring slots that still carry the previous tile's cells
+    int planes_here = RING;                                // planes shipped since the last tile switch
 
     auto unpatch_slot = [&](float* tile) {
 #pragma unroll
@@ -260,115 +548,87 @@ vox_fill_kernel(const float* __restrict__ feat, const int* __restrict__ ws, int 
             tile[__ldg(oldW + L.off_cell + sg) - old_cell_lo] = 0.f;
     };
 
-    for (long long u = u_begin; u < u_end;) {
-        const long long bt = u / planes;
-        const int p0 = (int)(u - bt * planes);
-        const int p1 = (int)min((long long)planes, p0 + (u_end - u));
-        u += p1 - p0;
-        const int t = (int)(bt % ntiles);
-        const int b = (int)(bt / ntiles);
+    for (int it = 0;; it ^= 1) {
+        const int item = s_item[it];
+        if (item >= total_items) break;
+        if (tid == 0) s_item[it ^ 1] = atomicAdd(work_counter, 1);      // next item; read after this item's barriers
+        const int bt = item / groups;
+        const int p0 = (item - bt * groups) * kPlaneGroup;
+        const int p1 = min(planes, p0 + kPlaneGroup);
+        const int t = bt % ntiles;
+        const int b = b0 + bt / ntiles;                    // B clouds starting at b0
         const int* W = ws + (size_t)b * L.stride;
-        const int* pid = W + L.off_pid;
         const int cell_lo = t * tile_cells;
         const int ncell = min(tile_cells, s - cell_lo);
-        const int sA = __ldg(W + L.off_tile + t), sB = __ldg(W + L.off_tile + t + 1);
 
-        if (curW != nullptr) {
-            if (stale > 0 || prev_planes < kRing) {
-                // the previous item did not cycle through the whole ring: clean everything the slow way
-                if (tid == 0) ri_bulk_wait_read<0>();
-                __syncthreads();
-                for (int k2 = 0; k2 < kRing; ++k2) {
-                    float* tile = sring + k2 * tile_cells;
-                    if (stale > 0) unpatch_slot(tile);
+        if (bt != cur_bt) {
+            const int sA = __ldg(W + L.off_tile + t), sB = __ldg(W + L.off_tile + t + 1);
+            if (curW != nullptr) {
+                if (stale > 0 || planes_here < RING) {
+                    // the previous tile did not cycle through the whole ring: clean everything the slow way
+                    if (tid == 0) ri_bulk_wait_read<0>();
+                    __syncthreads();
+                    for (int k2 = 0; k2 < RING; ++k2) {
+                        float* tile = sring + k2 * tile_cells;
+                        if (stale > 0) unpatch_slot(tile);
 #pragma unroll
-                    for (int q = 0; q < kSegCache; ++q)
-                        if (seg[q].cnt > 0) tile[seg[q].off] = 0.f;
-                    for (int sg = extra_lo + tid; sg < extra_hi; sg += kFillThreads)
-                        tile[__ldg(curW + L.off_cell + sg) - cur_cell_lo] = 0.f;
-                }
-                __syncthreads();
-                stale = 0;
+                        for (int q = 0; q < kSegCache; ++q)
+                            if (seg[q].cnt > 0) tile[seg[q].off] = 0.f;
+                        for (int sg = extra_lo + tid; sg < extra_hi; sg += kFillThreads)
+                            tile[__ldg(curW + L.off_cell + sg) - cur_cell_lo] = 0.f;
+                    }
+                    __syncthreads();
+                    stale = 0;
 #pragma unroll
-                for (int q = 0; q < kSegCache; ++q) old_off[q] = -1;
-                old_extra_lo = old_extra_hi = 0;
-            } else {
+                    for (int q = 0; q < kSegCache; ++q) old_off[q] = -1;
+                    old_extra_lo = old_extra_hi = 0;
+                } else {
 #pragma unroll
-                for (int q = 0; q < kSegCache; ++q) old_off[q] = seg[q].cnt > 0 ? seg[q].off : -1;
-                old_extra_lo = extra_lo; old_extra_hi = extra_hi; old_cell_lo = cur_cell_lo; oldW = curW;
-                stale = kRing;
-            }
-        }
-        // this item's table entries -> registers
-#pragma unroll
-        for (int q = 0; q < kSegCache; ++q) {
-            const int sg = sA + tid + q * kFillThreads;
-            seg[q].cnt = 0;
-            if (sg < sB) {
-                seg[q].off = __ldg(W + L.off_cell + sg) - cell_lo;
-                seg[q].st = __ldg(W + L.off_start + sg);
-                seg[q].cnt = __ldg(W + L.off_start + sg + 1) - seg[q].st;
-            }
-        }
-        extra_lo = min(sB, sA + kSegCache * kFillThreads); extra_hi = sB; cur_cell_lo = cell_lo; curW = W;
-        prev_planes = p1 - p0;
-
-        // undefined points of this cloud (ind == -1): edge rows are (0, feat); done by whoever owns tile 0's planes
-        if (edge != nullptr && t == 0) {
-            const int nvalid = __ldg(W + L.off_meta + 1);
-            for (int u = nvalid + tid; u < N; u += kFillThreads) {
-                const int i = __ldg(pid + u);
-                for (int p = p0; p < min(p1, C); ++p) {
-                    edge[((size_t)b * 2 * C + p) * N + i] = 0.f;
-                    edge[((size_t)b * 2 * C + C + p) * N + i] = __ldg(feat + ((size_t)b * C + p) * N + i);
+                    for (int q = 0; q < kSegCache; ++q) old_off[q] = seg[q].cnt > 0 ? seg[q].off : -1;
+                    old_extra_lo = extra_lo; old_extra_hi = extra_hi; old_cell_lo = cur_cell_lo; oldW = curW;
+                    stale = RING;
                 }
             }
+            // this tile's table entries -> registers
+#pragma unroll
+            for (int q = 0; q < kSegCache; ++q) {
+                const int sg = sA + tid + q * kFillThreads;
+                seg[q].cnt = 0;
+                if (sg < sB) {
+                    seg[q].off = __ldg(W + L.off_cell + sg) - cell_lo;
+                    seg[q].sg = sg;
+                    seg[q].cnt = __ldg(W + L.off_start + sg + 1) - __ldg(W + L.off_start + sg);
+                }
+            }
+            extra_lo = min(sB, sA + kSegCache * kFillThreads); extra_hi = sB; cur_cell_lo = cell_lo; curW = W;
+            cur_bt = bt;
+            planes_here = 0;
         }
+        planes_here += p1 - p0;
+        const float* Mb = means + (size_t)b * C * ucap;
 
-        // Planes are handled in batches of kPlaneBatch: the gathers of a whole batch (independent loads, one per
-        // plane and point) are issued together, so their latency is paid once per batch, not once per 32 KB tile.
+        // Planes are handled in batches of kPlaneBatch: the table reads of a whole batch (independent, coalesced
+        // loads, one per plane and cell) are issued together, so their latency is paid once per batch.
         for (int pb = p0; pb < p1; pb += kPlaneBatch) {
             float val[kSegCache][kPlaneBatch];
 #pragma unroll
             for (int q = 0; q < kSegCache; ++q) {
-                if (seg[q].cnt <= 0) continue;
-                const float inv = __fdiv_rn(1.0f, (float)seg[q].cnt);                       // vox.cu:66
 #pragma unroll
-                for (int j = 0; j < kPlaneBatch; ++j) val[q][j] = 0.f;
-                for (int u = seg[q].st; u < seg[q].st + seg[q].cnt; ++u) {                  // ascending point order
-                    const int i = __ldg(pid + u);
-                    float f[kPlaneBatch];
-#pragma unroll
-                    for (int j = 0; j < kPlaneBatch; ++j)
-                        f[j] = (pb + j < min(p1, C)) ? __ldg(feat + ((size_t)b * C + pb + j) * N + i) : 0.f;
-#pragma unroll
-                    for (int j = 0; j < kPlaneBatch; ++j)
-                        val[q][j] = __fadd_rn(val[q][j], __fmul_rn(f[j], inv));             // vox.cu:68-70
+                for (int j = 0; j < kPlaneBatch; ++j) {
+                    const int p = pb + j;
+                    val[q][j] = 0.f;
+                    if (seg[q].cnt > 0 && p < p1)
+                        val[q][j] = p < C ? __ldg(Mb + (size_t)p * ucap + seg[q].sg) : __int_as_float(seg[q].cnt);
                 }
-                if (edge != nullptr) {
-                    for (int u = seg[q].st; u < seg[q].st + seg[q].cnt; ++u) {
-                        const int i = __ldg(pid + u);
-#pragma unroll
-                        for (int j = 0; j < kPlaneBatch; ++j)
-                            if (pb + j < min(p1, C)) {
-                                const float f = __ldg(feat + ((size_t)b * C + pb + j) * N + i);
-                                edge[((size_t)b * 2 * C + pb + j) * N + i] = __fsub_rn(f, val[q][j]);
-                                edge[((size_t)b * 2 * C + C + pb + j) * N + i] = f;
-                            }
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < kPlaneBatch; ++j)
-                    if (pb + j >= C) val[q][j] = __int_as_float(seg[q].cnt);               // the count plane
             }
 #pragma unroll
             for (int j = 0; j < kPlaneBatch; ++j) {
                 const int p = pb + j;
                 if (p >= p1) break;
                 float* tile = sring + slot * tile_cells;
-                if (tid == 0) ri_bulk_wait_read<kRing - 1>();  // the copy that last used this slot has left smem
+                if (tid == 0) ri_bulk_wait_read<RING - 1>();  // the copy that last used this slot has left smem
                 __syncthreads();
-                if (stale > 0) {                                // first reuse of this slot since the item switch
+                if (stale > 0) {                                // first reuse of this slot since the tile switch
                     unpatch_slot(tile);
                     --stale;
                     __syncthreads();                            // an old cell may coincide with a new one of another thread
@@ -376,17 +636,10 @@ vox_fill_kernel(const float* __restrict__ feat, const int* __restrict__ ws, int 
 #pragma unroll
                 for (int q = 0; q < kSegCache; ++q)
                     if (seg[q].cnt > 0) tile[seg[q].off] = val[q][j];
-                if (extra_lo < extra_hi) {                      // cells beyond the register cache: direct path
-                    const float* Fp = feat + ((size_t)b * C + (p < C ? p : 0)) * N;
-                    float* er = (edge != nullptr && p < C) ? edge + ((size_t)b * 2 * C + p) * N : nullptr;
-                    float* ec = (edge != nullptr && p < C) ? edge + ((size_t)b * 2 * C + C + p) * N : nullptr;
-                    for (int sg = extra_lo + tid; sg < extra_hi; sg += kFillThreads) {
-                        SegRegs x;
-                        x.off = __ldg(W + L.off_cell + sg) - cell_lo;
-                        x.st = __ldg(W + L.off_start + sg);
-                        x.cnt = __ldg(W + L.off_start + sg + 1) - x.st;
-                        tile[x.off] = seg_value(x, p, C, N, Fp, pid, er, ec);
-                    }
+                for (int sg = extra_lo + tid; sg < extra_hi; sg += kFillThreads) {      // beyond the register cache
+                    const int off = __ldg(W + L.off_cell + sg) - cell_lo;
+                    tile[off] = p < C ? __ldg(Mb + (size_t)p * ucap + sg)
+                                      : __int_as_float(__ldg(W + L.off_start + sg + 1) - __ldg(W + L.off_start + sg));
                 }
                 ri_fence_proxy_async_smem();
                 __syncthreads();
@@ -396,9 +649,10 @@ vox_fill_kernel(const float* __restrict__ feat, const int* __restrict__ ws, int 
                     ri_bulk_store(dst, tile, (uint32_t)ncell * 4u);
                     ri_bulk_commit();
                 }
-                slot = (slot + 1 == kRing) ? 0 : slot + 1;
+                slot = (slot + 1 == RING) ? 0 : slot + 1;
             }
         }
+        __syncthreads();                                        // s_item[it ^ 1] is visible; s_item[it] may be rewritten
     }
     if (tid == 0) ri_bulk_wait<0>();
 }
@@ -458,6 +712,85 @@ VoxPlan vox_plan(int N, int r, const void* out, const void* cnt)
     return p;
 }
 
+size_t vox_ws_need(const VoxPlan& plan, int B, int C, int N)
+{
+    return (size_t)B * plan.L.stride * sizeof(int) + (size_t)B * C * ((N + 3) / 4 * 4) * sizeof(float) +
+           kMaxFillCalls * sizeof(int);                    // work counters of the fill launches
+}
+
+// K1 for all B clouds: ind + the per-cloud cell tables in the workspace
+template <bool SPH>
+int vox_prepare_launch(const void* coords, int B, int N, int r, int s, const VoxPlan& plan, int* ind, int* ws, cudaStream_t st)
+{
+    const size_t smem1 = (size_t)plan.P * (sizeof(unsigned long long) + sizeof(int));
+    if (smem1 + 1024 > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(vox_prepare_kernel<SPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        if (e != cudaSuccess) return (int)e;
+    }
+    vox_prepare_kernel<SPH><<<B, kPrepThreads, smem1, st>>>(coords, N, plan.P, r, s, plan.tile_cells, plan.ntiles, ind, ws);
+    RI_LAUNCH_CHECK();
+    return RI_OK;
+}
+
+// K2 for the clouds [b0, b1) of a batch of B whose tables are in the workspace: the compact table of cell means and,
+// when `edge` is given, the DGCNN edge features (whole-batch array).
+int vox_means_launch(const float* feat, int B, int C, int N, int b0, int b1, const VoxPlan& plan,
+                     float* edge, int* ws, cudaStream_t st)
+{
+    float* means = reinterpret_cast<float*>(ws + (size_t)B * plan.L.stride);
+    const int ucap = (N + 3) / 4 * 4;
+    const int nb = b1 - b0;
+    if (nb <= 0 || C <= 0) return RI_OK;
+    static bool carveout_set = false;
+    if (!carveout_set) {
+        ri_prefer_step_carveout(vox_means_kernel);
+        ri_prefer_step_carveout(vox_prepare_kernel<true>); ri_prefer_step_carveout(vox_prepare_kernel<false>);
+        carveout_set = true;
+    }
+    dim3 gm((C + kMeanChans - 1) / kMeanChans, nb);
+    // feature rows always staged (<= 128 KB at N = 4096); the means copy only while the CTA stays under ~100 KB
+    const int smem_means = (edge != nullptr && (size_t)kMeanChans * (N + 1 + ucap) * sizeof(float) <= 100 * 1024) ? 1 : 0;
+    const size_t smem_m = (size_t)kMeanChans * (N + 1 + (smem_means ? ucap : 0)) * sizeof(float);
+    if (smem_m > 48 * 1024) {
+        cudaError_t em = cudaFuncSetAttribute(vox_means_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
+        if (em != cudaSuccess) return (int)em;
+    }
+    vox_means_kernel<<<gm, kMeanThreads, smem_m, st>>>(feat, ws, b0, C, N, plan.ntiles, ucap, smem_means, means, edge);
+    RI_LAUNCH_CHECK();
+    return RI_OK;
+}
+
+// K3 for the clouds [b0, b1): the dense grid and the count grid from the tables and the means in the workspace.
+int vox_fill_launch(int B, int C, int N, int s, int b0, int b1, const VoxPlan& plan,
+                    float* out, int* cnt, int* ws, cudaStream_t st)
+{
+    float* means = reinterpret_cast<float*>(ws + (size_t)B * plan.L.stride);
+    const int ucap = (N + 3) / 4 * 4;
+    const int nb = b1 - b0;
+    if (nb <= 0) return RI_OK;
+    // one work counter per fill launch; slot chosen by the first cloud so that chunked launches never share one
+    int* counter = reinterpret_cast<int*>(means + (size_t)B * C * ucap) + (b0 % kMaxFillCalls);
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    const int sms = ri_num_sms();
+    int ring = kRing, ctas_per_sm = kFillCtasPerSm;
+    if (const char* ev = getenv("RI_FILL_RING")) { const int v = atoi(ev); if (v >= 3 && v <= 6) ring = v; }
+    if (const char* ev = getenv("RI_FILL_CTAS")) { const int v = atoi(ev); if (v >= 1 && v <= 2) ctas_per_sm = v; }
+    const size_t smem2 = (size_t)ring * plan.tile_cells * sizeof(float);
+    auto kern = ring == 3 ? vox_fill_kernel<3> : ring == 4 ? vox_fill_kernel<4> : ring == 5 ? vox_fill_kernel<5> : vox_fill_kernel<6>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e != cudaSuccess) return (int)e;
+    ri_prefer_step_carveout(kern);
+    const long long items = (long long)nb * plan.ntiles * ((C + 1 + kPlaneGroup - 1) / kPlaneGroup);
+    if (items > 0x7fffffffLL) return RI_ERR_UNSUPPORTED;
+    long long grid = (long long)ctas_per_sm * sms;
+    if (grid > items) grid = items;
+    kern<<<(unsigned)grid, kFillThreads, smem2, st>>>(means, ws, b0, nb, C, N, s, plan.tile_cells, plan.ntiles,
+                                                      ucap, counter, out, cnt);
+    RI_LAUNCH_CHECK();
+    return RI_OK;
+}
+
 template <bool SPH>
 int voxelize_impl(const float* feat, const void* coords, int B, int C, int N, int r,
                   float* out, int* ind, int* cnt, float* edge, void* workspace, size_t ws_bytes, cudaStream_t st)
@@ -469,29 +802,13 @@ int voxelize_impl(const float* feat, const void* coords, int B, int C, int N, in
     if (B == 0) return RI_OK;
     const VoxPlan plan = vox_plan(N, r, out, cnt);
     if (plan.tiled && N > 0) {
-        const size_t need = (size_t)B * plan.L.stride * sizeof(int);
-        if (workspace == nullptr || ws_bytes < need) return RI_ERR_WORKSPACE;
+        if (workspace == nullptr || ws_bytes < vox_ws_need(plan, B, C, N)) return RI_ERR_WORKSPACE;
         int* ws = reinterpret_cast<int*>(workspace);
-        const size_t smem1 = (size_t)plan.P * (sizeof(unsigned long long) + sizeof(int));
-        cudaError_t e;
-        if (smem1 + 1024 > 48 * 1024) {
-            e = cudaFuncSetAttribute(vox_prepare_kernel<SPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-            if (e != cudaSuccess) return (int)e;
-        }
-        vox_prepare_kernel<SPH><<<B, kPrepThreads, smem1, st>>>(coords, N, plan.P, r, s, plan.tile_cells, plan.ntiles, ind, ws);
-        RI_LAUNCH_CHECK();
-
-        const int sms = ri_num_sms();
-        const size_t smem2 = (size_t)kRing * plan.tile_cells * sizeof(float);
-        e = cudaFuncSetAttribute(vox_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        if (e != cudaSuccess) return (int)e;
-        const long long units = (long long)B * plan.ntiles * (C + 1);
-        long long grid = 2LL * sms;
-        if (grid > units) grid = units;
-        vox_fill_kernel<<<(unsigned)grid, kFillThreads, smem2, st>>>(feat, ws, B, C, N, s, plan.tile_cells, plan.ntiles,
-                                                                     out, cnt, edge);
-        RI_LAUNCH_CHECK();
-        return RI_OK;
+        const int rc = vox_prepare_launch<SPH>(coords, B, N, r, s, plan, ind, ws, st);
+        if (rc != RI_OK) return rc;
+        const int rc2 = vox_means_launch(feat, B, C, N, 0, B, plan, edge, ws, st);
+        if (rc2 != RI_OK) return rc2;
+        return vox_fill_launch(B, C, N, s, 0, B, plan, out, cnt, ws, st);
     }
     // fallback: memset + atomics (also covers N == 0)
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)B * C * s * sizeof(float), st);
@@ -514,13 +831,16 @@ int voxelize_impl(const float* feat, const void* coords, int B, int C, int N, in
 
 }  // namespace
 
-extern "C" size_t ri_voxelize_workspace_bytes(int B, int N, int r)
+extern "C" size_t ri_voxelize_workspace_bytes(int B, int C, int N, int r)
 {
     if (B <= 0 || N <= 0 || r <= 0) return 16;
+    if (C < 0) C = 0;
     const long long s = (long long)r * r * r;
     const int tile_cells = (int)(s < kTileCells ? s : kTileCells);
     const int ntiles = (int)((s + tile_cells - 1) / tile_cells);
-    return (size_t)B * vox_ws_layout(N, ntiles).stride * sizeof(int) + 16;
+    return (size_t)B * vox_ws_layout(N, ntiles).stride * sizeof(int) +            // per-cloud tables
+           (size_t)B * C * ((N + 3) / 4 * 4) * sizeof(float) +                   // compact cell means [B][C][<=N]
+           kMaxFillCalls * sizeof(int) + 16;                                      // work counters
 }
 
 extern "C" int ri_sph_voxelize_f32(const float* feat, const float* coords, int B, int C, int N, int r,
@@ -551,4 +871,97 @@ extern "C" int ri_cube_voxelize_edge_f32(const float* feat, const int* coords, i
 {
     if (edge == nullptr) return RI_ERR_BAD_ARG;
     return voxelize_impl<false>(feat, coords, B, C, N, r, out, ind, cnt, edge, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+// ---- two-phase form, for schedules that pipeline the grid through L2 ------------------------------------
+// prepare: ind [B,N] + the cell tables of ALL clouds (one launch); means: the compact cell-mean table (+ the DGCNN edge
+// features) and fill: the dense grid + count grid, both for the clouds [b0, b1) only.  A caller can then run  fill(chunk i) -> consumer(chunk i)  with chunks small enough that the
+// consumer (a devoxelize, a Conv3d) still finds the chunk's grid in the 126 MB L2.  Same workspace as the one-shot
+// calls; RI_ERR_UNSUPPORTED when the shape falls outside the tiled path (N > 4096, r^3 % 4 != 0, misaligned outputs):
+// use the one-shot entry points then.
+template <bool SPH>
+static int prepare_entry(const void* coords, int B, int C, int N, int r, int* ind, void* workspace, size_t ws_bytes, void* stream)
+{
+    if (B < 0 || C < 0 || N <= 0 || r <= 0 || r > 1024) return RI_ERR_BAD_ARG;
+    const long long s_ll = (long long)r * r * r;
+    if (s_ll > 0x7fffffffLL) return RI_ERR_UNSUPPORTED;
+    if (B == 0) return RI_OK;
+    const VoxPlan plan = vox_plan(N, r, nullptr, nullptr);
+    if (!plan.tiled) return RI_ERR_UNSUPPORTED;
+    if (workspace == nullptr || ws_bytes < vox_ws_need(plan, B, C, N)) return RI_ERR_WORKSPACE;
+    return vox_prepare_launch<SPH>(coords, B, N, r, (int)s_ll, plan, ind, reinterpret_cast<int*>(workspace), (cudaStream_t)stream);
+}
+
+extern "C" int ri_sph_voxelize_prepare_f32(const float* coords, int B, int C, int N, int r, int* ind,
+                                           void* workspace, size_t ws_bytes, void* stream)
+{
+    return prepare_entry<true>(coords, B, C, N, r, ind, workspace, ws_bytes, stream);
+}
+
+extern "C" int ri_cube_voxelize_prepare_f32(const int* coords, int B, int C, int N, int r, int* ind,
+                                            void* workspace, size_t ws_bytes, void* stream)
+{
+    return prepare_entry<false>(coords, B, C, N, r, ind, workspace, ws_bytes, stream);
+}
+
+extern "C" int ri_voxelize_means_f32(const float* feat, int B, int C, int N, int r, int b0, int b1, float* edge,
+                                     void* workspace, size_t ws_bytes, void* stream)
+{
+    if (B < 0 || C < 0 || N <= 0 || r <= 0 || r > 1024 || b0 < 0 || b1 > B || b0 > b1) return RI_ERR_BAD_ARG;
+    const long long s_ll = (long long)r * r * r;
+    if (s_ll > 0x7fffffffLL) return RI_ERR_UNSUPPORTED;
+    const VoxPlan plan = vox_plan(N, r, nullptr, nullptr);
+    if (!plan.tiled) return RI_ERR_UNSUPPORTED;
+    if (workspace == nullptr || ws_bytes < vox_ws_need(plan, B, C, N)) return RI_ERR_WORKSPACE;
+    return vox_means_launch(feat, B, C, N, b0, b1, plan, edge, reinterpret_cast<int*>(workspace), (cudaStream_t)stream);
+}
+
+extern "C" int ri_voxelize_fill_f32(int B, int C, int N, int r, int b0, int b1, float* out, int* cnt,
+                                    void* workspace, size_t ws_bytes, void* stream)
+{
+    if (B < 0 || C < 0 || N <= 0 || r <= 0 || r > 1024 || b0 < 0 || b1 > B || b0 > b1) return RI_ERR_BAD_ARG;
+    const long long s_ll = (long long)r * r * r;
+    if (s_ll > 0x7fffffffLL) return RI_ERR_UNSUPPORTED;
+    const VoxPlan plan = vox_plan(N, r, out, cnt);
+    if (!plan.tiled) return RI_ERR_UNSUPPORTED;
+    if (workspace == nullptr || ws_bytes < vox_ws_need(plan, B, C, N)) return RI_ERR_WORKSPACE;
+    return vox_fill_launch(B, C, N, (int)s_ll, b0, b1, plan, out, cnt, reinterpret_cast<int*>(workspace),
+                           (cudaStream_t)stream);
+}
+
+// ---- fused prefix of the voxel branch ----------------------------------------------------------------------------
+// ri_vox_prologue_f32 + ri_{sph,cube}_voxelize_prepare_f32 + ri_voxelize_means_f32 for all B clouds in ONE launch
+// (vox_front_kernel); ri_voxelize_fill_f32 completes the voxelization.  points [B,pstride,N] (pstride 3 or 6), mean [B,3]
+// (the caller's coords.mean(2)), shape 0 cube normalize=False / 1 cube normalize=True / 2 spherical, as ri_vox_prologue_f32.
+// Outputs norm_coords [B,3,N], vox_coords [B,3,N] (cube shapes), ind [B,N], edge [B,2C,N] (nullable) and the workspace
+// tables.  N <= 1024 and the tiled-path conditions, else RI_ERR_UNSUPPORTED (call the three entry points instead).
+extern "C" int ri_vox_front_f32(const float* points, int pstride, const float* mean, const float* feat,
+                                int B, int C, int N, int r, int shape, float eps, int norm_mode,
+                                float* norm_coords, int* vox_coords, int* ind, float* edge,
+                                void* workspace, size_t ws_bytes, void* stream)
+{
+    if (B < 0 || C < 0 || N <= 0 || r <= 0 || r > 1024 || (pstride != 3 && pstride != 6) || shape < 0 || shape > 2)
+        return RI_ERR_BAD_ARG;
+    if (norm_coords == nullptr || ind == nullptr || (shape != 2 && vox_coords == nullptr)) return RI_ERR_BAD_ARG;
+    const long long s_ll = (long long)r * r * r;
+    if (s_ll > 0x7fffffffLL || B > 65535) return RI_ERR_UNSUPPORTED;
+    if (B == 0) return RI_OK;
+    const VoxPlan plan = vox_plan(N, r, nullptr, nullptr);
+    if (!plan.tiled || N > kFrontMaxN) return RI_ERR_UNSUPPORTED;
+    if (workspace == nullptr || ws_bytes < vox_ws_need(plan, B, C, N)) return RI_ERR_WORKSPACE;
+    int* ws = reinterpret_cast<int*>(workspace);
+    float* means = reinterpret_cast<float*>(ws + (size_t)B * plan.L.stride);
+    const int ucap = (N + 3) / 4 * 4;
+    const size_t smem = (size_t)plan.P * (sizeof(unsigned long long) + sizeof(int)) + (size_t)(3 * N + 2) * sizeof(int) +
+                        (size_t)kMeanChans * (N + 4 + ucap) * sizeof(float);
+    auto kern = shape == 2 ? vox_front_kernel<true> : vox_front_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    ri_prefer_step_carveout(kern);
+    dim3 grid(C > 0 ? (C + kMeanChans - 1) / kMeanChans : 1, B);
+    kern<<<grid, kFrontThreads, smem, (cudaStream_t)stream>>>(points, pstride, mean, feat, C, N, plan.P, r, (int)s_ll,
+                                                              plan.tile_cells, plan.ntiles, shape, eps, norm_mode, ucap,
+                                                              norm_coords, vox_coords, ind, ws, means, edge);
+    RI_LAUNCH_CHECK();
+    return RI_OK;
 }

@@ -26,11 +26,18 @@ _check = _lib.check
 
 
 class FrontEnd:
-    KERNELS_PER_STEP = 6     # knn, ppf_gather, vox_prologue, vox_prepare, vox_fill (+fused edge features), devox
+    # knn+ppf (fused; else split, knn, ppf_gather), vox_prologue, vox_prepare + per grid chunk: vox_means (+edge
+    # features), vox_fill, devox
+    @property
+    def kernels_per_step(self):
+        return 3 + (3 if self._fused_front else 2 + 3 * self.grid_chunks)
     NORM_MODE = 1            # association of the 3-term radius sum that matches torch's norm kernel (see prologue.cu)
 
+    L2_CHUNK_BYTES = 40 << 20   # dense-grid bytes per pipeline chunk: small enough to still be in L2 when consumed
+
     def __init__(self, B, N, C, k=20, r=32, voxel_shape='spherical', normalize=False, eps=0.0,
-                 device='cuda', use_graph=True, overlap=True):
+                 device='cuda', use_graph=True, overlap=True, grid_chunks=None, devox_side_stream=True,
+                 knn_after_front=True, join_before_devox=True):
         if voxel_shape not in ('spherical', 'cube'):
             raise ValueError('voxel_shape must be "spherical" or "cube"')
         self.B, self.N, self.C, self.k, self.r = int(B), int(N), int(C), int(k), int(r)
@@ -41,6 +48,21 @@ class FrontEnd:
         self.use_graph, self.overlap = use_graph, overlap
         B, N, C, k, r = self.B, self.N, self.C, self.k, self.r
         s = r ** 3
+        # The grid goes through L2 in chunks of clouds: voxelize(chunk) -> devoxelize(chunk) while the chunk's dense
+        # grid (C * r^3 * 4 bytes per cloud) is still cache-resident, the next chunk's fill overlapping this chunk's
+        # devoxelize on a second stream.  Chunking needs the two-phase voxelizer (tiled path: N <= 4096, r^3 % 4 == 0).
+        per_cloud = max(1, (C + 1) * s * 4)
+        if grid_chunks is None:
+            # measured on B200 (tools/tune_step.py): the fixed cost of the extra launches outweighs the L2 hits at
+            # 32 x 1024-point clouds (1 chunk 268 us, 2 chunks 282 us, 4 chunks 295 us), so one chunk is the default
+            grid_chunks = 1
+        if N > 4096 or s % 4 != 0:
+            grid_chunks = 1
+        self.grid_chunks = int(max(1, min(grid_chunks, max(B, 1))))
+        self.devox_side_stream = bool(devox_side_stream)
+        self.knn_after_front, self.join_before_devox = bool(knn_after_front), bool(join_before_devox)
+        nb = -(-B // self.grid_chunks)
+        self._chunks = [(b0, min(B, b0 + nb)) for b0 in range(0, B, nb)]
         f32, i32, dev = torch.float32, torch.int32, self.device
         with torch.cuda.device(dev):
             # inputs
@@ -62,9 +84,13 @@ class FrontEnd:
             self.normals = torch.empty((B, 3, N), dtype=f32, device=dev)
             self.norm_coords = torch.empty((B, 3, N), dtype=f32, device=dev)
             self._vox_coords = torch.empty((B, 3, N), dtype=i32, device=dev)
-            self._ws_bytes = _L.ri_voxelize_workspace_bytes(B, N, r)
+            self._ws_bytes = _L.ri_voxelize_workspace_bytes(B, C, N, r)
             self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=dev)
-            self._side = torch.cuda.Stream(device=dev)
+            # the HBM-bound voxel branch runs on the (high-priority) main stream of the step, the ALU-bound k-NN/PPF
+            # branch on a low-priority side stream: when both have CTAs pending, the grid writer is placed first
+            self._side = torch.cuda.Stream(device=dev, priority=0)
+            self._main = torch.cuda.Stream(device=dev, priority=-1)
+            self._devox_stream = torch.cuda.Stream(device=dev, priority=-1)
             # host staging (pinned)
             self.h_points = torch.empty((B, 6, N), dtype=f32).pin_memory()
             self.h_features = torch.empty((B, C, N), dtype=f32).pin_memory()
@@ -72,6 +98,7 @@ class FrontEnd:
             self.h_devox = torch.empty((B, C, N), dtype=f32).pin_memory()
             self.h_edge = torch.empty((B, 2 * C, N), dtype=f32).pin_memory()
         self._graph = None
+        self._fused_front = self.grid_chunks == 1 and N <= 1024 and s % 4 == 0
 
     # bytes moved per host-facing call
     @property
@@ -86,51 +113,112 @@ class FrontEnd:
     def _branch_a(self):
         st = torch.cuda.current_stream().cuda_stream
         B, N, k = self.B, self.N, self.k
-        self.xyz.copy_(self.points[:, :3, :])
-        self.normals.copy_(self.points[:, 3:6, :])
+        _check(_L.ri_split_xyz_normals_f32(self.points.data_ptr(), B, N, self.xyz.data_ptr(), self.normals.data_ptr(), st),
+               'ri_split_xyz_normals')
         _check(_L.ri_knn_f32(self.xyz.data_ptr(), self.xyz.data_ptr(), B, 3, N, N, k,
                              self.knn_dist.data_ptr(), self.knn_idx.data_ptr(), st), 'ri_knn')
         _check(_L.ri_ppf_gather_f32(self.xyz.data_ptr(), self.normals.data_ptr(), self.knn_idx.data_ptr(), B, N, k,
                                     self.ppf.data_ptr(), st), 'ri_ppf_gather')
 
-    def _branch_b(self):
+    def _branch_b(self, join=None, fork=None):
         st = torch.cuda.current_stream().cuda_stream
         B, N, C, r = self.B, self.N, self.C, self.r
         # Coordinate prologue.  The per-cloud mean stays torch's own reduction (its summation order defines the bits
-        # the binning must see); everything after it is one kernel, bit-identical to the module shells
-        # (modules/voxelization.py) — asserted by tests/test_parity_gpu.py.
+        # the binning must see); everything after it is bit-identical to the module shells (modules/voxelization.py) —
+        # asserted by tests/test_parity_gpu.py.
         mean = self.points[:, :3, :].mean(2)
         sph = self.voxel_shape == 'spherical'
         shape = 2 if sph else (1 if self.normalize else 0)
+        if self.grid_chunks == 1 and N <= 1024 and (r ** 3) % 4 == 0:
+            # prologue + prepare + means/edge in one launch, then the grid writer
+            _check(_L.ri_vox_front_f32(self.points.data_ptr(), 6, mean.data_ptr(), self.features.data_ptr(), B, C, N, r,
+                                       shape, float(self.eps), self.NORM_MODE, self.norm_coords.data_ptr(),
+                                       self._vox_coords.data_ptr(), self.ind.data_ptr(), self.edge.data_ptr(),
+                                       self._ws.data_ptr(), self._ws_bytes, st), 'ri_vox_front')
+            if fork is not None:
+                # Branch A starts once the latency-bound prefix has had the machine to itself: started at t = 0 the
+                # long k-NN CTAs take the SMs first and stretch the prefix from 33 us to 85 us (tools/timeline.py);
+                # measured step 204 us this way, 216-224 us with both branches released together.
+                self._side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._side):
+                    fork()
+            _check(_L.ri_voxelize_fill_f32(B, C, N, r, 0, B, self.grid.data_ptr(), self.cnt.data_ptr(),
+                                           self._ws.data_ptr(), self._ws_bytes, st), 'ri_voxelize_fill')
+            if join is not None:
+                torch.cuda.current_stream().wait_stream(join)      # see below: the devoxelizer runs after branch A
+            self._devox(0, B, st)
+            return
         _check(_L.ri_vox_prologue_f32(self.points.data_ptr(), 6, mean.data_ptr(), B, N, r, shape, float(self.eps),
                                       self.NORM_MODE, None, None, self.norm_coords.data_ptr(),
                                       self._vox_coords.data_ptr(), st), 'ri_vox_prologue')
         nc = self.norm_coords
+        if self.grid_chunks == 1:
+            if sph:
+                _check(_L.ri_sph_voxelize_edge_f32(self.features.data_ptr(), nc.data_ptr(), B, C, N, r,
+                                                   self.grid.data_ptr(), self.ind.data_ptr(), self.cnt.data_ptr(),
+                                                   self.edge.data_ptr(), self._ws.data_ptr(), self._ws_bytes, st),
+                       'ri_sph_voxelize_edge')
+            else:
+                _check(_L.ri_cube_voxelize_edge_f32(self.features.data_ptr(), self._vox_coords.data_ptr(), B, C, N, r,
+                                                    self.grid.data_ptr(), self.ind.data_ptr(), self.cnt.data_ptr(),
+                                                    self.edge.data_ptr(), self._ws.data_ptr(), self._ws_bytes, st),
+                       'ri_cube_voxelize_edge')
+            if join is not None:
+                # the devoxelizer's gathers live off a large L1; CTAs of the k-NN branch (max-shared carveout) on the
+                # same SMs would force the small-L1 split on it (measured 54 us -> 300 us), so it starts after them
+                torch.cuda.current_stream().wait_stream(join)
+            self._devox(0, B, st)
+            return
         if sph:
-            _check(_L.ri_sph_voxelize_edge_f32(self.features.data_ptr(), nc.data_ptr(), B, C, N, r,
-                                               self.grid.data_ptr(), self.ind.data_ptr(), self.cnt.data_ptr(),
-                                               self.edge.data_ptr(), self._ws.data_ptr(), self._ws_bytes, st),
-                   'ri_sph_voxelize_edge')
-            _check(_L.ri_sph_trilinear_devox_f32(nc.data_ptr(), self.grid.data_ptr(), self.ind.data_ptr(), B, C, N, r,
-                                                 self.devox.data_ptr(), self.devox_inds.data_ptr(),
-                                                 self.devox_wgts.data_ptr(), st), 'ri_sph_trilinear_devox')
+            _check(_L.ri_sph_voxelize_prepare_f32(nc.data_ptr(), B, C, N, r, self.ind.data_ptr(),
+                                                  self._ws.data_ptr(), self._ws_bytes, st), 'ri_sph_voxelize_prepare')
         else:
-            _check(_L.ri_cube_voxelize_edge_f32(self.features.data_ptr(), self._vox_coords.data_ptr(), B, C, N, r,
-                                                self.grid.data_ptr(), self.ind.data_ptr(), self.cnt.data_ptr(),
-                                                self.edge.data_ptr(), self._ws.data_ptr(), self._ws_bytes, st),
-                   'ri_cube_voxelize_edge')
-            _check(_L.ri_trilinear_devox_f32(nc.data_ptr(), self.grid.data_ptr(), B, C, N, r,
-                                             self.devox.data_ptr(), self.devox_inds.data_ptr(),
-                                             self.devox_wgts.data_ptr(), st), 'ri_trilinear_devox')
+            _check(_L.ri_cube_voxelize_prepare_f32(self._vox_coords.data_ptr(), B, C, N, r, self.ind.data_ptr(),
+                                                   self._ws.data_ptr(), self._ws_bytes, st), 'ri_cube_voxelize_prepare')
+        main = torch.cuda.current_stream()
+        for (b0, b1) in self._chunks:
+            _check(_L.ri_voxelize_means_f32(self.features.data_ptr(), B, C, N, r, b0, b1, self.edge.data_ptr(),
+                                            self._ws.data_ptr(), self._ws_bytes, st), 'ri_voxelize_means')
+            _check(_L.ri_voxelize_fill_f32(B, C, N, r, b0, b1, self.grid.data_ptr(), self.cnt.data_ptr(),
+                                           self._ws.data_ptr(), self._ws_bytes, st), 'ri_voxelize_fill')
+            if self.devox_side_stream:
+                self._devox_stream.wait_stream(main)
+                with torch.cuda.stream(self._devox_stream):
+                    self._devox(b0, b1, self._devox_stream.cuda_stream)
+            else:
+                self._devox(b0, b1, st)
+        if self.devox_side_stream:
+            main.wait_stream(self._devox_stream)
+
+    def _devox(self, b0, b1, st):
+        """Devoxelize the clouds [b0, b1) of the batch (pointer offsets into the whole-batch arrays)."""
+        N, C, r = self.N, self.C, self.r
+        s = r ** 3
+        nb = b1 - b0
+        nc, g = self.norm_coords.data_ptr() + b0 * 3 * N * 4, self.grid.data_ptr() + b0 * C * s * 4
+        outs = self.devox.data_ptr() + b0 * C * N * 4
+        inds, wgts = self.devox_inds.data_ptr() + b0 * 8 * N * 4, self.devox_wgts.data_ptr() + b0 * 8 * N * 4
+        if self.voxel_shape == 'spherical':
+            _check(_L.ri_sph_trilinear_devox_f32(nc, g, self.ind.data_ptr() + b0 * N * 4, nb, C, N, r, outs, inds, wgts, st),
+                   'ri_sph_trilinear_devox')
+        else:
+            _check(_L.ri_trilinear_devox_f32(nc, g, nb, C, N, r, outs, inds, wgts, st), 'ri_trilinear_devox')
 
     def _step(self):
         if self.overlap:
-            main = torch.cuda.current_stream()
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
-                self._branch_a()
-            self._branch_b()
-            main.wait_stream(self._side)
+            cur = torch.cuda.current_stream()
+            self._main.wait_stream(cur)
+            self._side.wait_stream(cur)
+            if self.knn_after_front and self._fused_front:
+                with torch.cuda.stream(self._main):
+                    self._branch_b(join=self._side if self.join_before_devox else None, fork=self._branch_a)
+            else:
+                with torch.cuda.stream(self._side):
+                    self._branch_a()
+                with torch.cuda.stream(self._main):
+                    self._branch_b(join=self._side if self.join_before_devox else None)
+            cur.wait_stream(self._main)
+            cur.wait_stream(self._side)
         else:
             self._branch_a()
             self._branch_b()

@@ -209,7 +209,7 @@ def _voxelize(fn, what, features, coords, r, coord_dtype):
         out = torch.empty((B, C, s), dtype=torch.float32, device=dev)
         ind = torch.empty((B, N), dtype=torch.int32, device=dev)
         cnt = torch.empty((B, s), dtype=torch.int32, device=dev)
-        nbytes = _L.ri_voxelize_workspace_bytes(B, N, r)
+        nbytes = _L.ri_voxelize_workspace_bytes(B, C, N, r)
         ws = _workspace(dev, nbytes)
         _check(fn(features.data_ptr(), coords.data_ptr(), B, C, N, r, out.data_ptr(), ind.data_ptr(), cnt.data_ptr(),
                   ws.data_ptr(), ws.numel(), _stream()), what)
@@ -236,7 +236,7 @@ def _voxelize_edge(fn, what, features, coords, r, coord_dtype):
         ind = torch.empty((B, N), dtype=torch.int32, device=dev)
         cnt = torch.empty((B, s), dtype=torch.int32, device=dev)
         edge = torch.empty((B, 2 * C, N), dtype=torch.float32, device=dev)
-        ws = _workspace(dev, _L.ri_voxelize_workspace_bytes(B, N, r))
+        ws = _workspace(dev, _L.ri_voxelize_workspace_bytes(B, C, N, r))
         _check(fn(features.data_ptr(), coords.data_ptr(), B, C, N, r, out.data_ptr(), ind.data_ptr(), cnt.data_ptr(),
                   edge.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), what)
     return out, ind, cnt, edge
@@ -374,6 +374,35 @@ def voxel_edge_gather(avg: torch.Tensor, features: torch.Tensor, inds: torch.Ten
 def _(avg, features, inds):
     B, C, N = features.shape
     return features.new_empty((B, 2 * C, N))
+
+
+@torch.library.custom_op("ri::knn_ppf", mutates_args=())
+def knn_ppf(xyz: torch.Tensor, normals: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Self-query k-NN and the PPF of every (point, neighbour) pair: xyz, normals [B,3,N] -> dist [B,k,N], idx [B,k,N],
+    ppf [B,4,k,N].  One fused kernel while N <= 2048 and k <= 32, the k-NN + gather/PPF pair otherwise (same values)."""
+    _req(xyz, "xyz", torch.float32); _req(normals, "normals", torch.float32)
+    dev = _same_device(xyz, normals)
+    B, c, N = xyz.shape
+    if c != 3 or tuple(normals.shape) != (B, 3, N):
+        raise RuntimeError("xyz and normals must both be [B,3,N]")
+    with torch.cuda.device(dev):
+        d = torch.empty((B, k, N), dtype=torch.float32, device=dev)
+        i = torch.empty((B, k, N), dtype=torch.int32, device=dev)
+        out = torch.empty((B, 4, k, N), dtype=torch.float32, device=dev)
+        if N <= 2048 and k <= 32:
+            _check(_L.ri_knn_ppf_f32(xyz.data_ptr(), normals.data_ptr(), 3 * N, B, N, k, d.data_ptr(), i.data_ptr(),
+                                     out.data_ptr(), _stream()), "ri_knn_ppf")
+        else:
+            _knn_dir(xyz, xyz, B, 3, N, N, k, d, i, dev)
+            _check(_L.ri_ppf_gather_f32(xyz.data_ptr(), normals.data_ptr(), i.data_ptr(), B, N, k, out.data_ptr(), _stream()),
+                   "ri_ppf_gather")
+    return d, i, out
+
+
+@knn_ppf.register_fake
+def _(xyz, normals, k):
+    B, c, N = xyz.shape
+    return xyz.new_empty((B, k, N)), xyz.new_empty((B, k, N), dtype=torch.int32), xyz.new_empty((B, 4, k, N))
 
 
 # ---------------------------------------------------------------------------------------------- matcher

@@ -58,6 +58,8 @@ def test_ctypes_table_matches_header(built_lib):
                 assert t is ctypes.c_void_p, (name, a)
             elif a.startswith("size_t"):
                 assert t is ctypes.c_size_t, (name, a)
+            elif a.startswith("long long"):
+                assert t is ctypes.c_longlong, (name, a)
             elif a.startswith("float"):
                 assert t is ctypes.c_float, (name, a)
             else:
@@ -68,10 +70,11 @@ def test_abi_version_and_workspace_query(built_lib):
     built_lib.ri_abi_version.restype = ctypes.c_int
     assert built_lib.ri_abi_version() >= 1
     built_lib.ri_voxelize_workspace_bytes.restype = ctypes.c_size_t
-    built_lib.ri_voxelize_workspace_bytes.argtypes = [ctypes.c_int] * 3
-    small = built_lib.ri_voxelize_workspace_bytes(1, 1024, 32)
-    big = built_lib.ri_voxelize_workspace_bytes(32, 1024, 32)
-    assert 3 * 1024 * 4 <= small < big <= 32 * (4 * 1024 * 4 + 1024)
+    built_lib.ri_voxelize_workspace_bytes.argtypes = [ctypes.c_int] * 4
+    small = built_lib.ri_voxelize_workspace_bytes(1, 64, 1024, 32)
+    big = built_lib.ri_voxelize_workspace_bytes(32, 64, 1024, 32)
+    # per cloud: ~5 int tables of N entries + the compact means table C * N floats
+    assert 4 * 1024 * 4 + 64 * 1024 * 4 <= small < big <= 32 * (6 * 1024 * 4 + 64 * 1024 * 4 + 1024)
 
 
 def test_backend_has_reference_function_names():

@@ -97,6 +97,27 @@ def test_knn_backward(ri, ref_backend, golden_dir):
     assert scaled_err(A(g1), g["gradxyz1"]) <= TOL and scaled_err(A(g2), g["gradxyz2"]) <= TOL
 
 
+def test_knn_ppf_fused_equals_two_kernels(ri):
+    for B, N, k in [(4, 1024, 20), (3, 777, 16), (2, 2048, 32), (2, 40, 8), (1, 10, 20), (2, 3000, 20)]:
+        pts = clouds(B, N, 21 + N)
+        pts[:, :, N // 2:N // 2 + 3] = pts[:, :, :3]                  # duplicated points (ties) and ...
+        pts[:, 3:, 5] = 0.0                                             # ... a zero normal (degenerate column)
+        xyz, nrm = T(pts[:, :3].copy()), T(pts[:, 3:].copy())
+        d0, i0 = torch.ops.ri.knn_one(xyz, xyz, k)
+        p0 = torch.ops.ri.ppf_gather(xyz, nrm, i0)
+        d1, i1, p1 = torch.ops.ri.knn_ppf(xyz, nrm, k)
+        assert torch.equal(i0, i1) and torch.equal(d0, d1) and torch.equal(p0, p1)
+    # straight off the interleaved [B,6,N] batch (cloud stride 6N), as the front-end engine calls it
+    pts = T(clouds(4, 1024, 5)); B, N, k = 4, 1024, 20
+    L = ri._lib
+    d = torch.empty((B, k, N), device="cuda"); i = torch.empty((B, k, N), dtype=torch.int32, device="cuda")
+    o = torch.empty((B, 4, k, N), device="cuda")
+    L.check(L.lib.ri_knn_ppf_f32(pts.data_ptr(), pts.data_ptr() + 3 * N * 4, 6 * N, B, N, k, d.data_ptr(), i.data_ptr(),
+                                 o.data_ptr(), torch.cuda.current_stream().cuda_stream), "knn_ppf")
+    d1, i1, p1 = torch.ops.ri.knn_ppf(pts[:, :3].contiguous(), pts[:, 3:].contiguous(), k)
+    assert torch.equal(i, i1) and torch.equal(d, d1) and torch.equal(o, p1)
+
+
 # ================================================================================================ PPF
 def test_ppf_golden(ri, golden_dir, oracle):
     g = load_golden(golden_dir, "ppf.npz")
@@ -373,3 +394,39 @@ def test_pvconv_fused_edge_gradients_match_unfused(ri):
         ((grid1 * wg).sum() + (edge1 * we).sum()).backward()
         ((grid2 * wg).sum() + (edge2 * we).sum()).backward()
         assert scaled_err(A(f1.grad), A(f2.grad)) <= 1e-5
+
+
+@pytest.mark.parametrize("shape,normalize", [("spherical", False), ("cube", False), ("cube", True)])
+def test_fused_front_equals_separate_phases(ri, shape, normalize):
+    """ri_vox_front_f32 (prologue + prepare + means/edge in one launch) + fill == prologue, one-shot voxelize_edge."""
+    L = ri._lib
+    for B, N, C, r in [(5, 1024, 19, 16), (3, 777, 8, 32), (2, 100, 3, 8)]:
+        pts = T(clouds(B, N, 77 + N)); feat = T(np.random.default_rng(N).standard_normal((B, C, N)).astype(np.float32))
+        st = torch.cuda.current_stream().cuda_stream
+        mean = pts[:, :3, :].mean(2)
+        sh = 2 if shape == "spherical" else (1 if normalize else 0)
+        s = r ** 3
+        def bufs():
+            return dict(nc=torch.empty((B, 3, N), device="cuda"), vc=torch.zeros((B, 3, N), dtype=torch.int32, device="cuda"),
+                        ind=torch.empty((B, N), dtype=torch.int32, device="cuda"), edge=torch.empty((B, 2 * C, N), device="cuda"),
+                        out=torch.empty((B, C, s), device="cuda"), cnt=torch.empty((B, s), dtype=torch.int32, device="cuda"))
+        nws = L.lib.ri_voxelize_workspace_bytes(B, C, N, r)
+        a, b = bufs(), bufs()
+        ws = torch.empty(nws, dtype=torch.uint8, device="cuda")
+        L.check(L.lib.ri_vox_front_f32(pts.data_ptr(), 6, mean.data_ptr(), feat.data_ptr(), B, C, N, r, sh, 1e-3, 1,
+                                       a["nc"].data_ptr(), a["vc"].data_ptr(), a["ind"].data_ptr(), a["edge"].data_ptr(),
+                                       ws.data_ptr(), nws, st), "front")
+        L.check(L.lib.ri_voxelize_fill_f32(B, C, N, r, 0, B, a["out"].data_ptr(), a["cnt"].data_ptr(), ws.data_ptr(), nws, st), "fill")
+        ws2 = torch.empty(nws, dtype=torch.uint8, device="cuda")
+        L.check(L.lib.ri_vox_prologue_f32(pts.data_ptr(), 6, mean.data_ptr(), B, N, r, sh, 1e-3, 1, None, None,
+                                          b["nc"].data_ptr(), b["vc"].data_ptr(), st), "prologue")
+        if shape == "spherical":
+            L.check(L.lib.ri_sph_voxelize_edge_f32(feat.data_ptr(), b["nc"].data_ptr(), B, C, N, r, b["out"].data_ptr(),
+                                                   b["ind"].data_ptr(), b["cnt"].data_ptr(), b["edge"].data_ptr(),
+                                                   ws2.data_ptr(), nws, st), "vox")
+        else:
+            L.check(L.lib.ri_cube_voxelize_edge_f32(feat.data_ptr(), b["vc"].data_ptr(), B, C, N, r, b["out"].data_ptr(),
+                                                    b["ind"].data_ptr(), b["cnt"].data_ptr(), b["edge"].data_ptr(),
+                                                    ws2.data_ptr(), nws, st), "vox")
+        for k in a:
+            assert torch.equal(a[k], b[k]), (shape, normalize, B, N, C, r, k)
