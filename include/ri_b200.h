@@ -93,10 +93,14 @@ int ri_vox_prologue_f32(const float* points, int pstride, const float* mean, int
 int ri_knn_ppf_f32(const float* xyz, const float* normals, long long cloud_stride, int B, int N, int k,
                    float* dist, int* idx, float* ppf, void* stream);
 
-/* De-interleave points [B,6,N] (xyz | normal) into contiguous xyz [B,3,N] and normals [B,3,N]: the `.contiguous()`
+/* De-interleave points [B,6,N] (xyz | normal) into contiguous xyz [B,3,N] and normals [B,3,N] — the `.contiguous()`
  * copies of inputs[:, :3, :] / inputs[:, 3:, :] the reference's wrappers make (functional/knn.py:11-12,
- * functional/ppf.py:16-19), as one launch. */
-int ri_split_xyz_normals_f32(const float* points, int B, int N, float* xyz, float* normals, void* stream);
+ * functional/ppf.py:16-19) — and, optionally, the point-major packing packed [B,N,8] = (x,y,z,nx,ny,nz,0,0) (16-byte
+ * aligned) that ri_ppf_gather_packed_f32 reads.  Any of the three outputs may be null; one launch. */
+int ri_split_xyz_normals_f32(const float* points, int B, int N, float* xyz, float* normals, float* packed, void* stream);
+
+/* ri_ppf_gather_f32 on the packed cloud: no shared memory, neighbours fetched as two 16-byte gathers.  Same values. */
+int ri_ppf_gather_packed_f32(const float* packed, const int* idx, int B, int N, int k, float* out, void* stream);
 
 /* ---- voxelization ---------------------------------------------------------------------------------------
  * spherical_avg_voxelize_forward (spherical_voxelization/spherical_vox.cpp:17-46) and avg_voxelize_forward

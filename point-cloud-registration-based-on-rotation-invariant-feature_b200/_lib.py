@@ -23,7 +23,8 @@ SIGNATURES = {
     "ri_ppf_gather_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "ri_knn_ppf_f32": (_I, [_P, _P, ctypes.c_longlong, _I, _I, _I, _P, _P, _P, _P]),
     "ri_vox_prologue_f32": (_I, [_P, _I, _P, _I, _I, _I, _I, ctypes.c_float, _I, _P, _P, _P, _P, _P]),
-    "ri_split_xyz_normals_f32": (_I, [_P, _I, _I, _P, _P, _P]),
+    "ri_split_xyz_normals_f32": (_I, [_P, _I, _I, _P, _P, _P, _P]),
+    "ri_ppf_gather_packed_f32": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "ri_voxelize_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "ri_sph_voxelize_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
     "ri_cube_voxelize_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),

@@ -89,6 +89,27 @@ ppf_gather_kernel(const float* __restrict__ xyz, const float* __restrict__ norma
     }
 }
 
+// The same fused gather + PPF without any shared memory: the cloud comes pre-packed as two float4 per point
+// ((x, y, z, nx), (ny, nz, -, -); ri_split_xyz_normals_f32 writes it), so a neighbour is two 16-byte gathers that use
+// whole 32-byte sectors and hit L1/L2 (a cloud is 32 KB).  With no shared memory and 40-odd registers the kernel fits
+// next to anything — in the front-end step it runs alongside the devoxelizer, whose max-L1 carveout it shares.
+__global__ void __launch_bounds__(kGatherThreads)
+ppf_gather_packed_kernel(const float4* __restrict__ packed, const int* __restrict__ idx, int N, int k, float* __restrict__ out)
+{
+    const int b = blockIdx.y;
+    const size_t kN = (size_t)k * N;
+    const size_t w = (size_t)blockIdx.x * kGatherThreads + threadIdx.x;     // s * N + i : lanes walk consecutive centres
+    if (w >= kN) return;
+    const int i = (int)(w % N);
+    const float4* P = packed + (size_t)b * 2 * N;
+    const int j = __ldg(idx + (size_t)b * kN + w);
+    const float4 a = __ldg(P + 2 * i), aq = __ldg(P + 2 * i + 1);
+    const float4 p = __ldg(P + 2 * j), pq = __ldg(P + 2 * j + 1);
+    const Ppf4 r = ppf_column(a.x, a.y, a.z, a.w, aq.x, aq.y, p.x, p.y, p.z, p.w, pq.x, pq.y);
+    float* O = out + (size_t)b * 4 * kN + w;
+    O[0] = r.a1; O[kN] = r.a2; O[2 * kN] = r.a3; O[3 * kN] = r.dn;
+}
+
 }  // namespace
 
 extern "C" int ri_ppf_f32(const float* coords, const float* center, const float* normals,
@@ -132,6 +153,20 @@ extern "C" int ri_ppf_gather_f32(const float* xyz, const float* normals, const i
     } else {
         ppf_gather_kernel<false><<<grid, kGatherThreads, 0, st>>>(xyz, normals, idx, N, k, centres, out);
     }
+    RI_LAUNCH_CHECK();
+    return RI_OK;
+}
+
+// packed [B,N,8] floats = (x, y, z, nx, ny, nz, 0, 0) per point (16-byte aligned), idx [B,k,N] -> out [B,4,k,N];
+// same values as ri_ppf_gather_f32.
+extern "C" int ri_ppf_gather_packed_f32(const float* packed, const int* idx, int B, int N, int k, float* out, void* stream)
+{
+    if (B < 0 || N < 0 || k <= 0 || ((uintptr_t)packed & 15) != 0) return RI_ERR_BAD_ARG;
+    if (B > 65535) return RI_ERR_UNSUPPORTED;
+    if (B == 0 || N == 0) return RI_OK;
+    const size_t kN = (size_t)k * N;
+    dim3 grid((unsigned)((kN + kGatherThreads - 1) / kGatherThreads), B);
+    ppf_gather_packed_kernel<<<grid, kGatherThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(packed), idx, N, k, out);
     RI_LAUNCH_CHECK();
     return RI_OK;
 }

@@ -87,51 +87,44 @@ extern "C" int ri_vox_prologue_f32(const float* points, int pstride, const float
 
 // De-interleave a [B, 6, N] (xyz | normal) batch into the contiguous xyz [B,3,N] and normals [B,3,N] planes the k-NN and
 // PPF kernels take — the `.contiguous()` copies of the slices inputs[:, :3, :] / inputs[:, 3:, :] that the reference's
-// wrappers make (functional/knn.py:11-12, functional/ppf.py:16-19), as one launch.
+// wrappers make (functional/knn.py:11-12, functional/ppf.py:16-19) — and, optionally, the point-major packing
+// packed [B,N,8] = (x, y, z, nx, ny, nz, 0, 0) that ri_ppf_gather_packed_f32 gathers from; one launch.
 namespace {
 __global__ void __launch_bounds__(256)
-split6_kernel(const float4* __restrict__ points, size_t quads_per_half, float4* __restrict__ xyz, float4* __restrict__ normals)
-{
-    // per cloud the first 3N floats are xyz, the next 3N the normals: a straight vectorised copy
-    const size_t b = blockIdx.y;
-    const float4* P = points + b * 2 * quads_per_half;
-    for (size_t i = blockIdx.x * 256 + threadIdx.x; i < quads_per_half; i += (size_t)gridDim.x * 256) {
-        xyz[b * quads_per_half + i] = P[i];
-        normals[b * quads_per_half + i] = P[quads_per_half + i];
-    }
-}
-__global__ void __launch_bounds__(256)
-split6_scalar_kernel(const float* __restrict__ points, size_t half, float* __restrict__ xyz, float* __restrict__ normals)
+split6_kernel(const float* __restrict__ points, int N, float* __restrict__ xyz, float* __restrict__ normals,
+              float4* __restrict__ packed)
 {
     const size_t b = blockIdx.y;
-    const float* P = points + b * 2 * half;
-    for (size_t i = blockIdx.x * 256 + threadIdx.x; i < half; i += (size_t)gridDim.x * 256) {
-        xyz[b * half + i] = P[i];
-        normals[b * half + i] = P[half + i];
+    const float* P = points + b * 6 * N;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < N; i += gridDim.x * 256) {
+        float v[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) v[a] = P[(size_t)a * N + i];
+        if (xyz != nullptr) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) xyz[b * 3 * N + (size_t)a * N + i] = v[a];
+        }
+        if (normals != nullptr) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) normals[b * 3 * N + (size_t)a * N + i] = v[3 + a];
+        }
+        if (packed != nullptr) {
+            packed[(b * N + i) * 2] = make_float4(v[0], v[1], v[2], v[3]);
+            packed[(b * N + i) * 2 + 1] = make_float4(v[4], v[5], 0.f, 0.f);
+        }
     }
 }
 }  // namespace
 
-extern "C" int ri_split_xyz_normals_f32(const float* points, int B, int N, float* xyz, float* normals, void* stream)
+extern "C" int ri_split_xyz_normals_f32(const float* points, int B, int N, float* xyz, float* normals, float* packed,
+                                        void* stream)
 {
-    if (B < 0 || N < 0 || B > 65535) return RI_ERR_BAD_ARG;
+    if (B < 0 || N < 0 || B > 65535 || ((uintptr_t)packed & 15) != 0) return RI_ERR_BAD_ARG;
     if (B == 0 || N == 0) return RI_OK;
     static bool carveout_set = false;
-    if (!carveout_set) {
-        ri_prefer_step_carveout(split6_kernel); ri_prefer_step_carveout(split6_scalar_kernel);
-        carveout_set = true;
-    }
-    const size_t half = (size_t)3 * N;
-    const bool vec = (half % 4 == 0) && (((uintptr_t)points | (uintptr_t)xyz | (uintptr_t)normals) % 16 == 0);
-    if (vec) {
-        const size_t quads = half / 4;
-        dim3 grid((unsigned)((quads + 255) / 256 > 8 ? 8 : (quads + 255) / 256), B);
-        split6_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(points), quads,
-                                                              reinterpret_cast<float4*>(xyz), reinterpret_cast<float4*>(normals));
-    } else {
-        dim3 grid((unsigned)((half + 255) / 256 > 8 ? 8 : (half + 255) / 256), B);
-        split6_scalar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, half, xyz, normals);
-    }
+    if (!carveout_set) { ri_prefer_step_carveout(split6_kernel); carveout_set = true; }
+    dim3 grid((unsigned)((N + 255) / 256 > 16 ? 16 : (N + 255) / 256), B);
+    split6_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, N, xyz, normals, reinterpret_cast<float4*>(packed));
     RI_LAUNCH_CHECK();
     return RI_OK;
 }

@@ -82,6 +82,7 @@ class FrontEnd:
             self.edge = torch.empty((B, 2 * C, N), dtype=f32, device=dev)
             self.xyz = torch.empty((B, 3, N), dtype=f32, device=dev)
             self.normals = torch.empty((B, 3, N), dtype=f32, device=dev)
+            self._packed = torch.empty((B, N, 8), dtype=f32, device=dev)      # (x,y,z,nx,ny,nz,0,0) per point
             self.norm_coords = torch.empty((B, 3, N), dtype=f32, device=dev)
             self._vox_coords = torch.empty((B, 3, N), dtype=i32, device=dev)
             self._ws_bytes = _L.ri_voxelize_workspace_bytes(B, C, N, r)
@@ -110,15 +111,22 @@ class FrontEnd:
         return (self.h_ppf.numel() + self.h_devox.numel() + self.h_edge.numel()) * 4
 
     # ------------------------------------------------------------------ the step, enqueued on current stream(s)
-    def _branch_a(self):
+    def _knn(self):
         st = torch.cuda.current_stream().cuda_stream
         B, N, k = self.B, self.N, self.k
-        _check(_L.ri_split_xyz_normals_f32(self.points.data_ptr(), B, N, self.xyz.data_ptr(), self.normals.data_ptr(), st),
-               'ri_split_xyz_normals')
+        _check(_L.ri_split_xyz_normals_f32(self.points.data_ptr(), B, N, self.xyz.data_ptr(), self.normals.data_ptr(),
+                                           self._packed.data_ptr(), st), 'ri_split_xyz_normals')
         _check(_L.ri_knn_f32(self.xyz.data_ptr(), self.xyz.data_ptr(), B, 3, N, N, k,
                              self.knn_dist.data_ptr(), self.knn_idx.data_ptr(), st), 'ri_knn')
-        _check(_L.ri_ppf_gather_f32(self.xyz.data_ptr(), self.normals.data_ptr(), self.knn_idx.data_ptr(), B, N, k,
-                                    self.ppf.data_ptr(), st), 'ri_ppf_gather')
+
+    def _ppf(self):
+        st = torch.cuda.current_stream().cuda_stream
+        _check(_L.ri_ppf_gather_packed_f32(self._packed.data_ptr(), self.knn_idx.data_ptr(), self.B, self.N, self.k,
+                                           self.ppf.data_ptr(), st), 'ri_ppf_gather_packed')
+
+    def _branch_a(self):
+        self._knn()
+        self._ppf()
 
     def _branch_b(self, join=None, fork=None):
         st = torch.cuda.current_stream().cuda_stream
@@ -136,16 +144,22 @@ class FrontEnd:
                                        self._vox_coords.data_ptr(), self.ind.data_ptr(), self.edge.data_ptr(),
                                        self._ws.data_ptr(), self._ws_bytes, st), 'ri_vox_front')
             if fork is not None:
-                # Branch A starts once the latency-bound prefix has had the machine to itself: started at t = 0 the
+                # The k-NN starts once the latency-bound prefix has had the machine to itself: started at t = 0 the
                 # long k-NN CTAs take the SMs first and stretch the prefix from 33 us to 85 us (tools/timeline.py);
                 # measured step 204 us this way, 216-224 us with both branches released together.
                 self._side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(self._side):
-                    fork()
+                    self._knn()
             _check(_L.ri_voxelize_fill_f32(B, C, N, r, 0, B, self.grid.data_ptr(), self.cnt.data_ptr(),
                                            self._ws.data_ptr(), self._ws_bytes, st), 'ri_voxelize_fill')
             if join is not None:
-                torch.cuda.current_stream().wait_stream(join)      # see below: the devoxelizer runs after branch A
+                torch.cuda.current_stream().wait_stream(join)      # see below: the devoxelizer runs after the k-NN
+            if fork is not None:
+                # PPF (no shared memory, fp64-ALU bound) next to the devoxelizer (gather bound): both run with the
+                # default max-L1 carveout, so they share the SMs once the max-shared kernels are gone
+                self._side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._side):
+                    self._ppf()
             self._devox(0, B, st)
             return
         _check(_L.ri_vox_prologue_f32(self.points.data_ptr(), 6, mean.data_ptr(), B, N, r, shape, float(self.eps),

@@ -118,6 +118,23 @@ def test_knn_ppf_fused_equals_two_kernels(ri):
     assert torch.equal(i, i1) and torch.equal(d, d1) and torch.equal(o, p1)
 
 
+def test_split_and_packed_ppf(ri):
+    L = ri._lib
+    st = torch.cuda.current_stream().cuda_stream
+    for B, N, k in [(4, 1024, 20), (3, 777, 7), (2, 50, 20)]:
+        pts = T(clouds(B, N, 31 + N))
+        xyz = torch.empty((B, 3, N), device="cuda"); nrm = torch.empty((B, 3, N), device="cuda")
+        packed = torch.empty((B, N, 8), device="cuda")
+        L.check(L.lib.ri_split_xyz_normals_f32(pts.data_ptr(), B, N, xyz.data_ptr(), nrm.data_ptr(), packed.data_ptr(), st), "split")
+        assert torch.equal(xyz, pts[:, :3].contiguous()) and torch.equal(nrm, pts[:, 3:].contiguous())
+        assert torch.equal(packed[:, :, :6], pts.permute(0, 2, 1).contiguous()) and bool((packed[:, :, 6:] == 0).all())
+        _, idx = torch.ops.ri.knn_one(xyz, xyz, k)
+        want = torch.ops.ri.ppf_gather(xyz, nrm, idx)
+        got = torch.empty_like(want)
+        L.check(L.lib.ri_ppf_gather_packed_f32(packed.data_ptr(), idx.data_ptr(), B, N, k, got.data_ptr(), st), "ppf_packed")
+        assert torch.equal(got, want)
+
+
 # ================================================================================================ PPF
 def test_ppf_golden(ri, golden_dir, oracle):
     g = load_golden(golden_dir, "ppf.npz")

@@ -19,32 +19,21 @@ class Traced(ri_b200.FrontEnd):
         if name not in self.names:
             self.names.append(name)
         check(L.ri_debug_stamp(self.stamps.data_ptr() + 8 * self.names.index(name), st), "stamp")
-    def _branch_a(self):
-        st = torch.cuda.current_stream().cuda_stream
-        B, N, k = self.B, self.N, self.k
-        self._stamp("A0 start")
-        check(L.ri_split_xyz_normals_f32(self.points.data_ptr(), B, N, self.xyz.data_ptr(), self.normals.data_ptr(), st), "split")
-        check(L.ri_knn_f32(self.xyz.data_ptr(), self.xyz.data_ptr(), B, 3, N, N, k, self.knn_dist.data_ptr(), self.knn_idx.data_ptr(), st), "knn")
-        self._stamp("A2 knn done")
-        check(L.ri_ppf_gather_f32(self.xyz.data_ptr(), self.normals.data_ptr(), self.knn_idx.data_ptr(), B, N, k, self.ppf.data_ptr(), st), "ppf")
+    def _knn(self):
+        self._stamp("A0 knn start")
+        super()._knn()
+        self._stamp("A1 knn done")
+    def _ppf(self):
+        self._stamp("A2 ppf start")
+        super()._ppf()
         self._stamp("A3 ppf done")
-    def _branch_b(self, join=None):
-        st = torch.cuda.current_stream().cuda_stream
-        B, N, C, r = self.B, self.N, self.C, self.r
-        self._stamp("B0 start")
-        mean = self.points[:, :3, :].mean(2)
-        self._stamp("B1 mean done")
-        check(L.ri_vox_front_f32(self.points.data_ptr(), 6, mean.data_ptr(), self.features.data_ptr(), B, C, N, r, 0, 0.0, 1,
-                                 self.norm_coords.data_ptr(), self._vox_coords.data_ptr(), self.ind.data_ptr(), self.edge.data_ptr(),
-                                 self._ws.data_ptr(), self._ws_bytes, st), "front")
-        self._stamp("B3 front done")
-        check(L.ri_voxelize_fill_f32(B, C, N, r, 0, B, self.grid.data_ptr(), self.cnt.data_ptr(), self._ws.data_ptr(), self._ws_bytes, st), "fill")
-        self._stamp("B4 fill done")
-        if join is not None:
-            torch.cuda.current_stream().wait_stream(join)
-        self._stamp("B5 joined A")
-        self._devox(0, B, st)
+    def _devox(self, b0, b1, st):
+        self._stamp("B5 devox start")
+        super()._devox(b0, b1, st)
         self._stamp("B6 devox done")
+    def _branch_b(self, join=None, fork=None):
+        self._stamp("B0 start")
+        super()._branch_b(join=join, fork=fork)
 
 fes = []
 for q in range(3):

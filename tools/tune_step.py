@@ -16,7 +16,7 @@ def engines(**kw):
     for q in range(RING):
         fe = ri_b200.FrontEnd(B, N, C, k=k, r=r, voxel_shape=shape, **kw)
         fe.load(*data[q]); fe.forward(); fes.append(fe)
-        L.ri_split_xyz_normals_f32(fe.points.data_ptr(), B, N, fe.xyz.data_ptr(), fe.normals.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        L.ri_split_xyz_normals_f32(fe.points.data_ptr(), B, N, fe.xyz.data_ptr(), fe.normals.data_ptr(), fe._packed.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     return fes
 
@@ -30,6 +30,7 @@ def timeit(fn, fes, n=100):
     return e0.elapsed_time(e1) / n * 1e3
 
 st = torch.cuda.current_stream().cuda_stream
+s2 = torch.cuda.Stream()
 fes = engines(use_graph=False, overlap=False, grid_chunks=1)
 def knn(fe):
     assert L.ri_knn_f32(fe.xyz.data_ptr(), fe.xyz.data_ptr(), B, 3, N, N, k, fe.knn_dist.data_ptr(), fe.knn_idx.data_ptr(), st) == 0
@@ -37,6 +38,14 @@ print("knn          : %8.2f us" % timeit(knn, fes))
 def ppf(fe):
     assert L.ri_ppf_gather_f32(fe.xyz.data_ptr(), fe.normals.data_ptr(), fe.knn_idx.data_ptr(), B, N, k, fe.ppf.data_ptr(), st) == 0
 print("ppf gather   : %8.2f us" % timeit(ppf, fes))
+def ppfp(fe):
+    assert L.ri_ppf_gather_packed_f32(fe._packed.data_ptr(), fe.knn_idx.data_ptr(), B, N, k, fe.ppf.data_ptr(), st) == 0
+print("ppf packed   : %8.2f us" % timeit(ppfp, fes))
+def devox_ppf(fe):
+    cur = torch.cuda.current_stream(); s2.wait_stream(cur)
+    with torch.cuda.stream(s2):
+        assert L.ri_ppf_gather_packed_f32(fe._packed.data_ptr(), fe.knn_idx.data_ptr(), B, N, k, fe.ppf.data_ptr(), s2.cuda_stream) == 0
+    fe._devox(0, B, st); cur.wait_stream(s2)
 def knnppf(fe):
     assert L.ri_knn_ppf_f32(fe.points.data_ptr(), fe.points.data_ptr() + 3 * N * 4, 6 * N, B, N, k, fe.knn_dist.data_ptr(), fe.knn_idx.data_ptr(), fe.ppf.data_ptr(), st) == 0
 print("knn+ppf fused: %8.2f us" % timeit(knnppf, fes))
@@ -64,7 +73,6 @@ def fill(fe):
 def fill_edge(fe):
     means_edge(fe); fill_only(fe)
 # concurrency probe: the two branches' heavy kernels on two streams, eager
-s2 = torch.cuda.Stream()
 def both(fe):
     cur = torch.cuda.current_stream()
     s2.wait_stream(cur)
@@ -93,6 +101,7 @@ print("means+fill                         : %8.2f us" % timeit(fill, fes))
 print("means(+edge)+fill                  : %8.2f us" % timeit(fill_edge, fes))
 print("knn || means+fill (2 streams)      : %8.2f us" % timeit(both, fes))
 print("knn || devox (2 streams)           : %8.2f us" % timeit(both_devox, fes))
+print("devox || ppf packed (2 streams)    : %8.2f us" % timeit(devox_ppf, fes))
 print("devox whole batch (grid cold)      : %8.2f us" % timeit(lambda fe: fe._devox(0, B, st), fes))
 for after in (False, True):
     for join in (True, False):
