@@ -295,3 +295,80 @@ class FrontEnd:
         edge = 4 * N + 4 * C * N + 4 * C * N + 8 * C * N
         return {'knn_ppf': B * knn_ppf, 'voxelize': B * vox, 'devox': B * devox, 'edge': B * edge,
                 'total': B * (knn_ppf + vox + devox + edge)}
+
+
+class FrontEndPipeline:
+    """Host-facing streaming form of the engine: `depth` FrontEnd slots, each with its own pinned host buffers and device
+    buffers, driven by three streams so that consecutive calls overlap — while slot i computes, slot i+1's inputs go up
+    (H2D) and slot i-1's outputs come down (D2H; PCIe is full duplex).  Every call still moves its own inputs host->device
+    and its own outputs device->host; only the waiting is taken out.
+
+        pipe = FrontEndPipeline(B, N, C, depth=3, ...)
+        s = pipe.acquire()                  # next slot, its previous results have been handed back
+        pipe.slot(s).h_points[...] = ...    # fill the pinned inputs
+        pipe.submit(s)                      # H2D -> step -> D2H, asynchronous
+        out = pipe.result(s)                # {'ppf', 'devox', 'edge'} pinned host tensors (waits for that slot only)
+    """
+
+    def __init__(self, B, N, C, depth=3, device='cuda', **kw):
+        self.depth = int(depth)
+        self.device = torch.device(device)
+        self.slots = [FrontEnd(B, N, C, device=device, **kw) for _ in range(self.depth)]
+        with torch.cuda.device(self.device):
+            self._up = torch.cuda.Stream(device=self.device)
+            self._run = torch.cuda.Stream(device=self.device)
+            self._down = torch.cuda.Stream(device=self.device)
+            mk = lambda: [torch.cuda.Event() for _ in range(self.depth)]
+            self._ev_up, self._ev_run, self._ev_down = mk(), mk(), mk()
+            self._busy = [False] * self.depth
+            self._next = 0
+            for fe in self.slots:                 # capture the graphs up front (capture cannot overlap other work)
+                with torch.cuda.stream(self._run):
+                    fe.forward()
+            torch.cuda.synchronize(self.device)
+
+    def slot(self, s):
+        return self.slots[s]
+
+    def acquire(self):
+        """Next slot in round-robin order; blocks until the results of its previous submission have landed."""
+        s = self._next
+        self._next = (s + 1) % self.depth
+        if self._busy[s]:
+            self._ev_down[s].synchronize()
+            self._busy[s] = False
+        return s
+
+    def submit(self, s):
+        fe = self.slots[s]
+        with torch.cuda.device(self.device):
+            # the slot's device inputs are free once its previous step has run; its device outputs once they were copied
+            self._up.wait_event(self._ev_run[s])
+            with torch.cuda.stream(self._up):
+                fe.points.copy_(fe.h_points, non_blocking=True)
+                fe.features.copy_(fe.h_features, non_blocking=True)
+                self._ev_up[s].record(self._up)
+            self._run.wait_event(self._ev_up[s])
+            self._run.wait_event(self._ev_down[s])
+            with torch.cuda.stream(self._run):
+                fe.forward()
+                self._ev_run[s].record(self._run)
+            self._down.wait_event(self._ev_run[s])
+            with torch.cuda.stream(self._down):
+                fe.h_ppf.copy_(fe.ppf, non_blocking=True)
+                fe.h_devox.copy_(fe.devox, non_blocking=True)
+                fe.h_edge.copy_(fe.edge, non_blocking=True)
+                self._ev_down[s].record(self._down)
+        self._busy[s] = True
+
+    def result(self, s):
+        self._ev_down[s].synchronize()
+        self._busy[s] = False
+        fe = self.slots[s]
+        return {'ppf': fe.h_ppf, 'devox': fe.h_devox, 'edge': fe.h_edge}
+
+    def drain(self):
+        for s in range(self.depth):
+            if self._busy[s]:
+                self._ev_down[s].synchronize()
+                self._busy[s] = False

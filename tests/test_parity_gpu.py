@@ -447,3 +447,32 @@ def test_fused_front_equals_separate_phases(ri, shape, normalize):
                                                     ws2.data_ptr(), nws, st), "vox")
         for k in a:
             assert torch.equal(a[k], b[k]), (shape, normalize, B, N, C, r, k)
+
+
+def test_pipeline_matches_single_engine(ri):
+    """FrontEndPipeline (overlapped H2D / step / D2H over 3 slots) returns what FrontEnd.__call__ returns, call after call."""
+    B, N, C, k, r = 4, 1024, 9, 20, 16
+    fe = ri.FrontEnd(B, N, C, k=k, r=r, voxel_shape="cube")
+    pipe = ri.FrontEndPipeline(B, N, C, depth=3, k=k, r=r, voxel_shape="cube")
+    want = []
+    batches = [(clouds(B, N, 100 + q), np.random.default_rng(q).standard_normal((B, C, N)).astype(np.float32)) for q in range(7)]
+    for pts, ft in batches:
+        out = fe(pts, ft)
+        want.append({n: v.clone() for n, v in out.items()})
+    tickets = []
+    got = [None] * len(batches)
+    for q, (pts, ft) in enumerate(batches):
+        s = pipe.acquire()
+        if len(tickets) >= pipe.depth:                       # the slot being reused: its result was collected below
+            pass
+        pipe.slot(s).h_points.copy_(torch.from_numpy(pts)); pipe.slot(s).h_features.copy_(torch.from_numpy(ft))
+        pipe.submit(s)
+        tickets.append((q, s))
+        if len(tickets) == pipe.depth:                       # collect the oldest before its slot comes round again
+            q0, s0 = tickets.pop(0)
+            got[q0] = {n: v.clone() for n, v in pipe.result(s0).items()}
+    for q0, s0 in tickets:
+        got[q0] = {n: v.clone() for n, v in pipe.result(s0).items()}
+    for a, b in zip(want, got):
+        for n in a:
+            assert torch.equal(a[n], b[n]), n
