@@ -217,6 +217,19 @@ def run_ours(args, rank, world, local):
     vox_gbs = alg["voxelize"] / (ms_vox / vox_steps * 1e-3) / 1e9
     step_gbs = alg["total"] / (ms / args.steps * 1e-3) / 1e9
 
+    # ---- registration matcher (BASELINE configs[2]: 256 pairs x 1024 x 1024 x 512 over 8 GPUs = 32 pairs per GPU), an
+    #      auxiliary figure: tcgen05 3xTF32 contraction + fused argmins, CUDA events, descriptors resident in HBM
+    MP, MC, Mn = 32, 512, 1024
+    g = torch.Generator(device=dev); g.manual_seed(4242 + rank)
+    d1 = torch.randn((MP, MC, Mn), device=dev, generator=g); d2 = torch.randn((MP, MC, Mn), device=dev, generator=g)
+    mm = ri_b200.matcher.MutualMatcher(MP, MC, Mn, Mn, device=dev)
+    for _ in range(3):
+        mm(d1, d2)
+    m_steps = 20
+    ms_match, w = timed(lambda i: mm(d1, d2), m_steps); windows.append(w)
+    ms_match /= m_steps
+    del mm, d1, d2
+
     if rank != 0:
         return
     sampler.stop()
@@ -245,6 +258,12 @@ def run_ours(args, rank, world, local):
                                        "api": "FrontEnd.run_staged()"}},
         "gpu_launches": engines[0].kernels_per_step * args.steps,
         "clocks": sampler.summary(windows),
+        "matcher": {"workload": "mutual-NN matching, %d pairs x %d x %d x %d per GPU (BASELINE configs[2] at 8 GPUs)" % (MP, Mn, Mn, MC),
+                    "pairs_per_s": world * MP / (ms_match * 1e-3), "ms_per_call": ms_match,
+                    "useful_tflops": world * 2.0 * MP * Mn * Mn * MC / (ms_match * 1e-3) / 1e12,
+                    "issued_tf32_tflops": world * 3 * 2.0 * MP * Mn * Mn * MC / (ms_match * 1e-3) / 1e12,
+                    "note": "3xTF32 split precision: three tensor-core products per useful one; includes the re-tiling "
+                            "pre-pass and the fp32 distance re-evaluation"},
     }
     if world == 1:
         line["cpu_baseline"] = cpu_port_baseline(wl, batches[0])

@@ -13,22 +13,28 @@
 //   * Precision: a single tf32/bf16 pass cannot hold the 1e-5 contract (nor stable argmins), so the product is the
 //     3xTF32 split  a = a_hi + a_lo  (a_hi = a with the low 13 mantissa bits cleared — representable in tf32 whatever
 //     the hardware does with the low bits —, a_lo = a - a_hi, exact in fp32),  a.b ~ hi.hi + hi.lo + lo.hi, fp32
-//     accumulation in TMEM: ~2^-22 relative per product, the order of sgemm's own rounding.
-//   * match_prep     per cloud: squared norms (accumulated in fp64, rounded once), the hi/lo split, and a re-tiling into
-//                    UMMA "canonical K-major, no swizzle" core-matrix images  T[kc][plane][row/8][k16/4][row%8][4 floats]
-//                    (kc = 16-channel chunk, plane = hi|lo).  An operand tile of R rows x 16 channels is then ONE
-//                    contiguous R*64-byte block, so the GEMM kernel stages operands with plain cp.async.bulk copies
-//                    (TMA engine, no tensor maps) and describes them with LBO = 128 B, SBO = 512 B.
+//     accumulation in TMEM.  The tensor core's accumulator adds truncate (measured 1.1e-5 of |f1|^2 + |f2|^2 on
+//     well-matched 512-channel descriptors — over the contract — while the ARGMINS agree with an fp64 evaluation), so
+//     this kernel decides WHO matches and match_finish reports HOW FAR, re-evaluating |f1_i - f2_j|^2 in fp32.
+//   * match_prep     per cloud: squared norms (accumulated in fp64, rounded once) and a re-tiling of the raw fp32
+//                    descriptors into UMMA "canonical K-major, no swizzle" core-matrix order
+//                    R[kc][row/8][k16/4][row%8][4 floats]  (kc = 16-channel chunk).  An operand tile of R rows x 16
+//                    channels is then ONE contiguous R*64-byte block: the GEMM kernel stages operands with plain
+//                    cp.async.bulk copies (TMA engine, no tensor maps) and describes them with LBO = 128 B, SBO = 512 B.
 //   * match_gemm     one CTA per 128 x 256 tile of a pair's distance matrix, 192 threads, warp-specialised:
-//                      warp 0 / lane 0   producer: 4-stage ring of 48 KB stages, mbarrier complete_tx
-//                      warp 1            TMEM allocator; lane 0 issues tcgen05.mma.kind::tf32 (M128 N256 K8), 6 per stage,
-//                                        tcgen05.commit releases the stage / publishes the accumulator
-//                      warps 2-5         epilogue: tcgen05.ld 32 columns at a time, d = (n1 + n2) - 2 acc, row argmin in
-//                                        registers, column argmin with redux.sync + ballot, merged across tiles by
-//                                        64-bit atomicMin on packed keys (ordered(d) << 32 | index): lowest index
-//                                        wins ties, as np.argmin does.
-//   * match_finish   per pair: unpack c1/c2, mutual mask, ordered compaction (idx1, idx2, count), and the distance of
-//                    every row's match recomputed as an fp32 FMA chain (what is reported, not the 3xTF32 value).
+//                      warp 4 / lane 0   TMA producer: 24 KB of raw fp32 per 16-channel stage, mbarrier complete_tx
+//                      warps 0-3         converters: split the stage IN shared memory (hi written back in place, lo to
+//                                        the second plane; fence.proxy.async; mbarrier arrive) — the first version
+//                                        loaded pre-split planes instead, 48 KB per stage against ~810 tensor-core
+//                                        cycles, i.e. 59 B/clk per SM where the L2 sustains ~42 (tensor pipe 39 %) —
+//                                        and afterwards run the epilogue: tcgen05.ld 32 columns at a time,
+//                                        d = (n1 + n2) - 2 acc, row argmin in registers, column argmin with redux.sync
+//                                        + ballot, merged across tiles by 64-bit atomicMin on packed keys
+//                                        (ordered(d) << 32 | index): lowest index wins ties, as np.argmin does
+//                      warp 5            TMEM allocator; lane 0 issues tcgen05.mma.kind::tf32 (M128 N256 K8), 6 per
+//                                        stage; tcgen05.commit releases the stage / publishes the accumulator
+//   * match_finish   per pair: unpack c1/c2, mutual mask, ordered compaction (idx1, idx2, count), and the fp32 distance
+//                    of every row's match from the re-tiled descriptors (64 contiguous bytes per row and chunk).
 #include "ri_common.cuh"
 
 namespace {
@@ -57,8 +63,8 @@ __host__ __device__ inline MatchWs match_ws_layout(int P, int C, int n1, int n2)
     w.n2p = round_up(n2 > 0 ? n2 : 1, kTileN);
     w.Cp = round_up(C > 0 ? C : 1, kChunkK);
     size_t o = 0;
-    w.img1 = o; o += (size_t)P * w.n1p * w.Cp * 2 * sizeof(float);
-    w.img2 = o; o += (size_t)P * w.n2p * w.Cp * 2 * sizeof(float);
+    w.img1 = o; o += (size_t)P * w.n1p * w.Cp * sizeof(float);
+    w.img2 = o; o += (size_t)P * w.n2p * w.Cp * sizeof(float);
     w.nrm1 = o; o += (size_t)P * w.n1p * sizeof(float);
     w.nrm2 = o; o += (size_t)P * w.n2p * sizeof(float);
     o = (o + 15) / 16 * 16;
@@ -75,58 +81,56 @@ __device__ __forceinline__ unsigned ordered_u32(float f)
 }
 
 // ------------------------------------------------------------------------------------------------ match_prep
-// One CTA = (cloud, tile of 256 rows).  Walks the channel chunks; per chunk the 16 x 256 block goes through shared
-// memory so that global reads are coalesced along the source's contiguous axis and image writes are 16-byte chunks in
-// address order.
-constexpr int kPrepRows = 256;
+// One CTA = (cloud, tile of 64 rows), 256 threads, one 16-byte chunk of the image per thread and channel chunk.  Per
+// chunk the 16 x 64 block goes through shared memory so that global reads are coalesced along the source's contiguous
+// axis and image writes are 16-byte chunks in address order.
+constexpr int kPrepRows = 64;
+constexpr int kPrepThreads = kPrepRows * 4;
 constexpr int kPrepLd = kPrepRows + 2;                       // 4*q*ld mod 32 = {0,8,16,24}: conflict-free chunk reads
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(kPrepThreads)
 match_prep_kernel(const float* __restrict__ desc, int C, int n, int npad, int Cp, int point_major,
                   float* __restrict__ img, float* __restrict__ nrm, unsigned long long* __restrict__ key)
 {
-    __shared__ float s[kChunkK * kPrepLd];
+    __shared__ float s[2][kChunkK * kPrepLd];
     const int cloud = blockIdx.y;
     const int r0 = blockIdx.x * kPrepRows;
-    const int u = threadIdx.x;                               // 16-byte chunk id inside the (256 rows x 16 ch) block
+    const int u = threadIdx.x;                               // 16-byte chunk id inside the (64 rows x 16 ch) block
     const int i_loc = ((u >> 5) << 3) | (u & 7);
     const int q = (u >> 3) & 3;
     const float* D = desc + (size_t)cloud * C * n;
-    float* I = img + (size_t)cloud * npad * Cp * 2;
-    const size_t plane = (size_t)npad * kChunkK;             // floats per (chunk, plane)
+    float* I = img + (size_t)cloud * npad * Cp;
+    const size_t plane = (size_t)npad * kChunkK;             // floats per chunk
+    const int nk = Cp / kChunkK;
     double acc = 0.0;
 
-    for (int kc = 0; kc < Cp / kChunkK; ++kc) {
-        __syncthreads();
+    auto stage = [&](int kc, float* dst) {
         if (!point_major) {                                  // [C, n]: lanes walk rows (contiguous)
-            for (int e = u; e < kChunkK * kPrepRows; e += 1024) {
-                const int c = e >> 8, i = e & 255;
+            for (int e = u; e < kChunkK * kPrepRows; e += kPrepThreads) {
+                const int c = e / kPrepRows, i = e % kPrepRows;
                 const int gc = kc * kChunkK + c, gi = r0 + i;
-                s[c * kPrepLd + i] = (gc < C && gi < n) ? D[(size_t)gc * n + gi] : 0.f;
+                dst[c * kPrepLd + i] = (gc < C && gi < n) ? __ldg(D + (size_t)gc * n + gi) : 0.f;
             }
         } else {                                             // [n, C]: lanes walk channels (contiguous)
-            for (int e = u; e < kChunkK * kPrepRows; e += 1024) {
+            for (int e = u; e < kChunkK * kPrepRows; e += kPrepThreads) {
                 const int c = e & 15, i = e >> 4;
                 const int gc = kc * kChunkK + c, gi = r0 + i;
-                s[c * kPrepLd + i] = (gc < C && gi < n) ? D[(size_t)gi * C + gc] : 0.f;
+                dst[c * kPrepLd + i] = (gc < C && gi < n) ? __ldg(D + (size_t)gi * C + gc) : 0.f;
             }
         }
-        __syncthreads();
-        float4 hi, lo;
-        float v[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            v[e] = s[(4 * q + e) * kPrepLd + i_loc];
-            acc = fma((double)v[e], (double)v[e], acc);
-        }
-        hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xffffe000u); lo.x = __fsub_rn(v[0], hi.x);
-        hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xffffe000u); lo.y = __fsub_rn(v[1], hi.y);
-        hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xffffe000u); lo.z = __fsub_rn(v[2], hi.z);
-        hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xffffe000u); lo.w = __fsub_rn(v[3], hi.w);
+    };
+    stage(0, s[0]);
+    for (int kc = 0; kc < nk; ++kc) {
+        __syncthreads();                                     // chunk kc staged; the other buffer is free again
+        if (kc + 1 < nk) stage(kc + 1, s[(kc + 1) & 1]);
+        const float* src = s[kc & 1];
+        float4 v;
+        v.x = src[(4 * q + 0) * kPrepLd + i_loc]; v.y = src[(4 * q + 1) * kPrepLd + i_loc];
+        v.z = src[(4 * q + 2) * kPrepLd + i_loc]; v.w = src[(4 * q + 3) * kPrepLd + i_loc];
+        acc = fma((double)v.x, (double)v.x, acc); acc = fma((double)v.y, (double)v.y, acc);
+        acc = fma((double)v.z, (double)v.z, acc); acc = fma((double)v.w, (double)v.w, acc);
         // image offset of row (r0 + i_loc), k-core q :  ((row / 8) * 4 + q) * 32 + (row % 8) * 4  floats
-        float* dst = I + (size_t)kc * 2 * plane + (size_t)(r0 >> 3) * 128 + (size_t)u * 4;
-        *reinterpret_cast<float4*>(dst) = hi;
-        *reinterpret_cast<float4*>(dst + plane) = lo;
+        *reinterpret_cast<float4*>(I + (size_t)kc * plane + (size_t)(r0 >> 3) * 128 + (size_t)u * 4) = v;
     }
     // squared norm of row i_loc: the four k-core partials sit in lanes u ^ 8, u ^ 16, u ^ 24
     acc += __shfl_xor_sync(0xffffffffu, acc, 8);
@@ -208,9 +212,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 struct GemmSmem {                                            // after the stage ring
     unsigned long long colkey[4][kTileN];                    // per epilogue warp, per column
     float n2[kTileN];
-    unsigned long long full[kStages], empty[kStages], accum;
+    unsigned long long raw[kStages], full[kStages], empty[kStages], accum;
     uint32_t tmem_base;
 };
+
+// hi / lo split of 16-byte k-core slots, in place: x -> (x & 0xffffe000) at the same address, x - hi in the lo plane.
+// All loads are issued before the first store (the compiler must assume the stores alias the later loads otherwise,
+// which serialises twelve load -> store round trips per stage).
+__device__ __forceinline__ void split4(float4 v, float4& h, float4& l)
+{
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = __fsub_rn(v.x, h.x);
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = __fsub_rn(v.y, h.y);
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = __fsub_rn(v.z, h.z);
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = __fsub_rn(v.w, h.w);
+}
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
@@ -222,54 +237,52 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     GemmSmem* S = reinterpret_cast<GemmSmem*>(smem + (size_t)kStages * kStageBytes);
     const uint32_t ring = ri_smem_u32(smem);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
     const int pair = blockIdx.z, m0 = blockIdx.y * kTileM, c0 = blockIdx.x * kTileN;
     const int nk = Cp / kChunkK;
+    // stage layout: [A hi 8 KB][A lo 8 KB][B hi 16 KB][B lo 16 KB]; the raw fp32 tiles land in the hi regions
+    constexpr int kAHi = 0, kALo = kABytes, kBHi = 2 * kABytes, kBLo = 2 * kABytes + kBBytes;
 
-    if (threadIdx.x == 0) {
+    if (t == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(ri_smem_u32(&S->full[s]), 1);
-            mbar_init(ri_smem_u32(&S->empty[s]), 1);
+            mbar_init(ri_smem_u32(&S->raw[s]), 1);           // TMA producer's expect_tx arrival + the bytes
+            mbar_init(ri_smem_u32(&S->full[s]), 4);          // one arrival per converter warp and stage (128 per-thread
+                                                             // arrivals serialise on the barrier word: 2.7k clk per stage)
+            mbar_init(ri_smem_u32(&S->empty[s]), 1);         // tcgen05.commit
         }
         mbar_init(ri_smem_u32(&S->accum), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         ri_fence_proxy_async_smem();
     }
-    if (warp == 1) {                                         // TMEM: 256 fp32 columns x 128 lanes
+    if (warp == 5) {                                         // TMEM: 256 fp32 columns x 128 lanes
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"(ri_smem_u32(&S->tmem_base)), "r"((uint32_t)kTileN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp >= 2) {
-        const int t = threadIdx.x - 64;
+    if (warp < 4)
         for (int j = t; j < kTileN; j += 128) S->n2[j] = nrm2[(size_t)pair * n2p + c0 + j];
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S->tmem_base;
 
-    if (warp == 0) {
-        if (lane == 0) {                                     // ---- producer
-            const uint8_t* A = reinterpret_cast<const uint8_t*>(img1) + (size_t)pair * n1p * Cp * 8;
-            const uint8_t* B = reinterpret_cast<const uint8_t*>(img2) + (size_t)pair * n2p * Cp * 8;
+    if (warp == 4) {
+        if (lane == 0) {                                     // ---- TMA producer: raw fp32 tiles, 24 KB per stage
+            const uint8_t* A = reinterpret_cast<const uint8_t*>(img1) + (size_t)pair * n1p * Cp * 4;
+            const uint8_t* B = reinterpret_cast<const uint8_t*>(img2) + (size_t)pair * n2p * Cp * 4;
             const size_t planeA = (size_t)n1p * kRowBytes, planeB = (size_t)n2p * kRowBytes;
             for (int kc = 0; kc < nk; ++kc) {
                 const int s = kc % kStages;
                 const uint32_t ph = (kc / kStages) & 1;
                 mbar_wait(ri_smem_u32(&S->empty[s]), ph ^ 1);
-                const uint32_t full = ri_smem_u32(&S->full[s]);
-                mbar_expect_tx(full, kStageBytes);
+                const uint32_t bar = ri_smem_u32(&S->raw[s]);
+                mbar_expect_tx(bar, kABytes + kBBytes);
                 const uint32_t dst = ring + s * kStageBytes;
-                const uint8_t* a = A + (size_t)kc * 2 * planeA + (size_t)m0 * kRowBytes;
-                const uint8_t* b = B + (size_t)kc * 2 * planeB + (size_t)c0 * kRowBytes;
-                bulk_g2s(dst, a, kABytes, full);
-                bulk_g2s(dst + kABytes, a + planeA, kABytes, full);
-                bulk_g2s(dst + 2 * kABytes, b, kBBytes, full);
-                bulk_g2s(dst + 2 * kABytes + kBBytes, b + planeB, kBBytes, full);
+                bulk_g2s(dst + kAHi, A + (size_t)kc * planeA + (size_t)m0 * kRowBytes, kABytes, bar);
+                bulk_g2s(dst + kBHi, B + (size_t)kc * planeB + (size_t)c0 * kRowBytes, kBBytes, bar);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 5) {
         if (lane == 0) {                                     // ---- MMA issuer
             for (int kc = 0; kc < nk; ++kc) {
                 const int s = kc % kStages;
@@ -280,10 +293,8 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
 #pragma unroll
                 for (int ks = 0; ks < kChunkK / 8; ++ks) {
                     const uint32_t koff = ks * 2 * kLBO;     // one K-step = two 16-byte k-cores
-                    const uint64_t a_hi = smem_desc(base + koff);
-                    const uint64_t a_lo = smem_desc(base + kABytes + koff);
-                    const uint64_t b_hi = smem_desc(base + 2 * kABytes + koff);
-                    const uint64_t b_lo = smem_desc(base + 2 * kABytes + kBBytes + koff);
+                    const uint64_t a_hi = smem_desc(base + kAHi + koff), a_lo = smem_desc(base + kALo + koff);
+                    const uint64_t b_hi = smem_desc(base + kBHi + koff), b_lo = smem_desc(base + kBLo + koff);
                     tc_mma_tf32(tmem, a_lo, b_hi, kIdesc, (kc | ks) != 0);      // small terms first
                     tc_mma_tf32(tmem, a_hi, b_lo, kIdesc, 1);
                     tc_mma_tf32(tmem, a_hi, b_hi, kIdesc, 1);
@@ -292,10 +303,42 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
             }
             tc_commit(ri_smem_u32(&S->accum));               // accumulator complete
         }
-    } else {                                                 // ---- epilogue (warps 2..5 -> TMEM lane groups 2,3,0,1)
-        const int qd = warp & 3;
-        const int row = qd * 32 + lane;
-        const int gi = m0 + row;
+    } else {
+        // ---- converters: thread t splits A-tile row t and B-tile rows t, t + 128 (4 k-core slots each) of every stage
+        const uint32_t slot_a = (uint32_t)(t >> 3) * kSBO + (uint32_t)(t & 7) * 16;        // row t inside a plane
+        const uint32_t slot_b1 = (uint32_t)((t + 128) >> 3) * kSBO + (uint32_t)(t & 7) * 16;
+        for (int kc = 0; kc < nk; ++kc) {
+            const int s = kc % kStages;
+            const uint32_t ph = (kc / kStages) & 1;
+            mbar_wait(ri_smem_u32(&S->raw[s]), ph);
+            uint8_t* st = smem + (size_t)s * kStageBytes;
+            float4 v[12];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                v[3 * q + 0] = *reinterpret_cast<const float4*>(st + kAHi + slot_a + q * kLBO);
+                v[3 * q + 1] = *reinterpret_cast<const float4*>(st + kBHi + slot_a + q * kLBO);
+                v[3 * q + 2] = *reinterpret_cast<const float4*>(st + kBHi + slot_b1 + q * kLBO);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 h, l;
+                split4(v[3 * q + 0], h, l);
+                *reinterpret_cast<float4*>(st + kAHi + slot_a + q * kLBO) = h;
+                *reinterpret_cast<float4*>(st + kALo + slot_a + q * kLBO) = l;
+                split4(v[3 * q + 1], h, l);
+                *reinterpret_cast<float4*>(st + kBHi + slot_a + q * kLBO) = h;
+                *reinterpret_cast<float4*>(st + kBLo + slot_a + q * kLBO) = l;
+                split4(v[3 * q + 2], h, l);
+                *reinterpret_cast<float4*>(st + kBHi + slot_b1 + q * kLBO) = h;
+                *reinterpret_cast<float4*>(st + kBLo + slot_b1 + q * kLBO) = l;
+            }
+            ri_fence_proxy_async_smem();                     // generic-proxy stores -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(ri_smem_u32(&S->full[s])) : "memory");
+        }
+        // ---- epilogue: warp w reads TMEM lanes [32w, 32w + 32) = tile rows, i.e. thread t <-> row t
+        const int gi = m0 + t;
         const bool row_ok = gi < n1;
         const float na = nrm1[(size_t)pair * n1p + gi];
         mbar_wait(ri_smem_u32(&S->accum), 0);
@@ -303,7 +346,7 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
         float best = 0.f; int best_j = -1;
         for (int cc = 0; cc < kTileN; cc += 32) {
             uint32_t v[32];
-            tmem_ld32(tmem + ((uint32_t)(qd * 32) << 16) + (uint32_t)cc, v);
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc, v);
             unsigned long long mine = ~0ull;
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
@@ -314,14 +357,13 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
                 const unsigned mn = __reduce_min_sync(0xffffffffu, key);
                 const unsigned who = __ballot_sync(0xffffffffu, key == mn);
                 if (lane == e)
-                    mine = ((unsigned long long)mn << 32) | (unsigned)(m0 + qd * 32 + (__ffs(who) - 1));
+                    mine = ((unsigned long long)mn << 32) | (unsigned)(m0 + warp * 32 + (__ffs(who) - 1));
             }
-            S->colkey[qd][cc + lane] = mine;
+            S->colkey[warp][cc + lane] = mine;
         }
         if (row_ok && best_j >= 0)
             atomicMin(rowkey + (size_t)pair * n1p + gi, ((unsigned long long)ordered_u32(best) << 32) | (unsigned)best_j);
         asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps
-        const int t = threadIdx.x - 64;
         for (int j = t; j < kTileN; j += 128) {
             if (c0 + j >= n2) continue;
             unsigned long long k0 = S->colkey[0][j];
@@ -332,19 +374,19 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == 5) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)kTileN) : "memory");
     }
 }
 
 // ------------------------------------------------------------------------------------------------ match_finish
-// One CTA per pair.  corr12[i] = argmin_j, corr21[j] = argmin_i, dist12[i] = fp32 distance of (i, corr12[i]) recomputed
-// with an FMA chain over the channels, (idx1, idx2)[0..count) = the mutual matches in ascending i, -1 beyond.
+// One CTA per pair.  corr12[i] = argmin_j, corr21[j] = argmin_i, (idx1, idx2)[0..count) = the mutual matches in ascending
+// i (-1 beyond), dist12[i] = |f1_i - f2_corr12[i]|^2 accumulated in fp32 from the re-tiled descriptors (per 16-channel
+// chunk a row is 4 x 16 B at a 128 B stride: whole sectors, where the channel-major source would cost 512 sectors a row).
 constexpr int kFinThreads = 512;
 __global__ void __launch_bounds__(kFinThreads)
-match_finish_kernel(const float* __restrict__ d1, const float* __restrict__ d2, int C, int n1, int n2, int n1p, int n2p,
-                    int point_major, const float* __restrict__ nrm1, const float* __restrict__ nrm2,
+match_finish_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int n1, int n2, int n1p, int n2p, int Cp,
                     const unsigned long long* __restrict__ rowkey, const unsigned long long* __restrict__ colkey,
                     int* __restrict__ corr12, int* __restrict__ corr21, float* __restrict__ dist12,
                     int* __restrict__ idx1, int* __restrict__ idx2, int* __restrict__ count)
@@ -355,8 +397,10 @@ match_finish_kernel(const float* __restrict__ d1, const float* __restrict__ d2, 
     const unsigned long long* RK = rowkey + (size_t)p * n1p;
     const unsigned long long* CK = colkey + (size_t)p * n2p;
     for (int j = tid; j < n2; j += kFinThreads) corr21[(size_t)p * n2 + j] = (int)(unsigned)(CK[j] & 0xffffffffu);
-    const float* F1 = d1 + (size_t)p * C * n1;
-    const float* F2 = d2 + (size_t)p * C * n2;
+    const float* I1 = img1 + (size_t)p * n1p * Cp;
+    const float* I2 = img2 + (size_t)p * n2p * Cp;
+    const size_t plane1 = (size_t)n1p * kChunkK, plane2 = (size_t)n2p * kChunkK;
+    const int nk = Cp / kChunkK;
     if (tid == 0) sbase = 0;
     __syncthreads();
     for (int i0 = 0; i0 < n1; i0 += kFinThreads) {
@@ -368,15 +412,21 @@ match_finish_kernel(const float* __restrict__ d1, const float* __restrict__ d2, 
             if (!sane) j = 0;
             corr12[(size_t)p * n1 + i] = j;
             mutual = (sane && (int)(unsigned)(CK[j] & 0xffffffffu) == i) ? 1 : 0;
-            float dot = 0.f;
-            if (point_major) {
-                const float* a = F1 + (size_t)i * C; const float* b = F2 + (size_t)j * C;
-                for (int c = 0; c < C; ++c) dot = __fmaf_rn(a[c], b[c], dot);
-            } else {
-                for (int c = 0; c < C; ++c) dot = __fmaf_rn(F1[(size_t)c * n1 + i], F2[(size_t)c * n2 + j], dot);
+            const float* a = I1 + (size_t)(i >> 3) * 128 + (size_t)(i & 7) * 4;
+            const float* b = I2 + (size_t)(j >> 3) * 128 + (size_t)(j & 7) * 4;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};                   // no cancellation between norms and dot product
+            for (int kc = 0; kc < nk; ++kc) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(a + (size_t)kc * plane1 + q * 32));
+                    const float4 y = __ldg(reinterpret_cast<const float4*>(b + (size_t)kc * plane2 + q * 32));
+                    float df = __fsub_rn(x.x, y.x); acc[0] = __fmaf_rn(df, df, acc[0]);
+                    df = __fsub_rn(x.y, y.y); acc[1] = __fmaf_rn(df, df, acc[1]);
+                    df = __fsub_rn(x.z, y.z); acc[2] = __fmaf_rn(df, df, acc[2]);
+                    df = __fsub_rn(x.w, y.w); acc[3] = __fmaf_rn(df, df, acc[3]);
+                }
             }
-            dist12[(size_t)p * n1 + i] =
-                __fmaf_rn(-2.0f, dot, __fadd_rn(nrm1[(size_t)p * n1p + i], nrm2[(size_t)p * n2p + j]));
+            dist12[(size_t)p * n1 + i] = __fadd_rn(__fadd_rn(acc[0], acc[1]), __fadd_rn(acc[2], acc[3]));
         }
         // ordered compaction of the mutual matches
         const unsigned bal = __ballot_sync(0xffffffffu, mutual);
@@ -426,9 +476,9 @@ extern "C" int ri_mutual_nn_tf32x3(const float* desc1, const float* desc2, int P
     unsigned long long* rowkey = reinterpret_cast<unsigned long long*>(ws + L.rowkey);
     unsigned long long* colkey = reinterpret_cast<unsigned long long*>(ws + L.colkey);
 
-    match_prep_kernel<<<dim3(L.n1p / kPrepRows, P), 1024, 0, st>>>(desc1, C, n1, L.n1p, L.Cp, point_major, img1, nrm1, rowkey);
+    match_prep_kernel<<<dim3(L.n1p / kPrepRows, P), kPrepThreads, 0, st>>>(desc1, C, n1, L.n1p, L.Cp, point_major, img1, nrm1, rowkey);
     RI_LAUNCH_CHECK();
-    match_prep_kernel<<<dim3(L.n2p / kPrepRows, P), 1024, 0, st>>>(desc2, C, n2, L.n2p, L.Cp, point_major, img2, nrm2, colkey);
+    match_prep_kernel<<<dim3(L.n2p / kPrepRows, P), kPrepThreads, 0, st>>>(desc2, C, n2, L.n2p, L.Cp, point_major, img2, nrm2, colkey);
     RI_LAUNCH_CHECK();
 
     const size_t smem = (size_t)kStages * kStageBytes + sizeof(GemmSmem) + 1024;
@@ -438,8 +488,8 @@ extern "C" int ri_mutual_nn_tf32x3(const float* desc1, const float* desc2, int P
         img1, img2, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp, rowkey, colkey);
     RI_LAUNCH_CHECK();
 
-    match_finish_kernel<<<P, kFinThreads, 0, st>>>(desc1, desc2, C, n1, n2, L.n1p, L.n2p, point_major, nrm1, nrm2,
-                                                   rowkey, colkey, corr12, corr21, dist12, idx1, idx2, count);
+    match_finish_kernel<<<P, kFinThreads, 0, st>>>(img1, img2, n1, n2, L.n1p, L.n2p, L.Cp, rowkey, colkey,
+                                                   corr12, corr21, dist12, idx1, idx2, count);
     RI_LAUNCH_CHECK();
     return RI_OK;
 }
