@@ -179,6 +179,19 @@ int ri_devox_backward_f32(const float* grad_y, const int* inds, const float* wgt
 int ri_voxel_edge_gather_f32(const float* avg, const float* feat, const int* inds, int B, int C, int N, int s,
                              float* out, void* stream);
 
+/* ---- ball query + grouping (the neighbourhood the shipped models use for local features) ----------
+ * ball_query_forward (ball_query/ball_query.cpp:6-30 -> ball_query_kernel ball_query.cu:19-50): for each of the M centres
+ * the first U points (in index order) with 1e-5 < d^2 < radius^2; the first hit fills the whole row, a centre without
+ * neighbours keeps zeros.  centers [B,3,M], points [B,3,N] -> neighbors [B,M,U] int32, fully overwritten.  Bit-exact. */
+int ri_ball_query_f32(const float* centers, const float* points, int B, int N, int M, float radius, int U,
+                      int* neighbors, void* stream);
+
+/* grouping_forward / grouping_backward (grouping/grouping.cu:18-44, 58-84): out [B,C,M,U] = feat[b, c, idx[b, m, u]];
+ * grad_x [B,C,N] += grad_y scattered through idx (float atomics, as the reference; grad_x is zeroed first). */
+int ri_grouping_f32(const float* feat, const int* idx, int B, int C, int N, int M, int U, float* out, void* stream);
+int ri_grouping_backward_f32(const float* grad_y, const int* idx, int B, int C, int N, int M, int U,
+                             float* grad_x, void* stream);
+
 /* ---- mutual-nearest-neighbour descriptor matching (datasets/deepgmr_mn40.py:232-244) ---------------------
  * find_correspondence_one_pair for P independent (source, target) pairs.
  * desc1, desc2: fp32 descriptors, channel-major [P,C,n1] / [P,C,n2] (what the feature extractor emits,

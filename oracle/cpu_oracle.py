@@ -192,6 +192,37 @@ def voxel_edge_gather(avg, features, inds):
     return out
 
 
+def ball_query(centers, points, radius, num_neighbors):
+    """ball_query/ball_query.cu:19-50: centers [B,3,M], points [B,3,N] -> int32 [B,M,U]."""
+    centers, points = _f(centers), _f(points)
+    B, _, M = centers.shape
+    N = points.shape[2]
+    out = np.empty((B, M, num_neighbors), np.int32)
+    lib().ri_oracle_ball_query.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_float, ctypes.c_int, ctypes.c_void_p]
+    lib().ri_oracle_ball_query(_p(centers), _p(points), B, N, M, float(radius), int(num_neighbors), _p(out))
+    return out
+
+
+def grouping(features, indices):
+    """grouping/grouping.cu:18-44: features [B,C,N], indices [B,M,U] -> [B,C,M,U]."""
+    features, indices = _f(features), _i(indices)
+    B, C, N = features.shape
+    _, M, U = indices.shape
+    out = np.empty((B, C, M, U), np.float32)
+    lib().ri_oracle_grouping(_p(features), _p(indices), B, C, N, M, U, _p(out))
+    return out
+
+
+def grouping_grad(grad_y, indices, N):
+    """grouping/grouping.cu:58-84: grad_y [B,C,M,U], indices [B,M,U] -> grad_x [B,C,N]."""
+    grad_y, indices = _f(grad_y), _i(indices)
+    B, C, M, U = grad_y.shape
+    out = np.empty((B, C, N), np.float32)
+    lib().ri_oracle_grouping_grad(_p(grad_y), _p(indices), B, C, N, M, U, _p(out))
+    return out
+
+
 def find_correspondence_one_pair(feat1, feat2):
     """datasets/deepgmr_mn40.py:232-244, restated with the same numpy calls (fp32 in, fp32 sgemm)."""
     diff = (np.power(np.linalg.norm(feat1, axis=1, keepdims=True), 2)

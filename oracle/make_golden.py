@@ -137,6 +137,22 @@ def main(out_dir):
                      f"r{r}_douts": A(douts), f"r{r}_dinds": A(dinds), f"r{r}_dwgts": A(dwgts), f"r{r}_dgy": dgy,
                      f"r{r}_dgx": A(dgx)})
     np.savez_compressed(os.path.join(out_dir, "cube.npz"), **cube)
+    # ---------------------------------------------------------------- ball query + grouping (+ backward)
+    bq = {}
+    pts = cloud(rng, 3, 400, "surface"); ctr = pts[:, :, :150].copy()
+    ctr[:, :, 140:] += 5.0                        # centres with no neighbour at all -> zero rows
+    pts[:, :, 300:310] = pts[:, :, 0:10]          # duplicates of centres 0..9: d2 = 0 excluded like the centre itself
+    pts[:, :, 310] = pts[:, :, 11] + np.float32(0.002)      # d2 ~ 1.2e-5: just above the 1e-5 lower bound
+    pts[:, :, 311] = pts[:, :, 12] + np.float32(0.0015)     # d2 ~ 6.75e-6: just below it
+    for name, (radius, u) in {"a": (0.3, 16), "b": (0.15, 64), "c": (2.0, 8)}.items():
+        idx = ref.ball_query(T(ctr), T(pts), radius, u)
+        feats = rng.standard_normal((3, 6, 400)).astype(np.float32)
+        grp = ref.grouping_forward(T(feats), idx)
+        gy = rng.standard_normal(A(grp).shape).astype(np.float32)
+        gx = ref.grouping_backward(T(gy), idx, 400)
+        bq.update({f"{name}_radius": radius, f"{name}_u": u, f"{name}_idx": A(idx), f"{name}_feat": feats,
+                   f"{name}_grp": A(grp), f"{name}_gy": gy, f"{name}_gx": A(gx)})
+    np.savez_compressed(os.path.join(out_dir, "ball_query.npz"), centers=ctr, points=pts, **bq)
     print("golden vectors written to", out_dir, sorted(os.listdir(out_dir)))
 
 

@@ -388,3 +388,55 @@ void ri_oracle_voxel_edge_gather(const float *avg, const float *feat, const int 
                 out[((size_t)b * 2 * C + C + c) * N + i] = f;
             }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Ball query.  PVCNN/modules/functional/src/ball_query/ball_query.cu:19-50 (+ torch::zeros output and
+ * r2 = radius * radius in float, ball_query.cpp:18-24).  centers [B,3,M], points [B,3,N] -> idx [B,M,U].
+ * d2 = fma(dz,dz, fma(dy,dy, dx*dx)) is the contraction in the reference's sm_100a SASS (FMUL dx, FFMA dy, FFMA dz);
+ * the lower bound is the double pow(10,-5) == 1e-5 for every float d2 (no float lies within a double ulp of it).
+ * -----------------------------------------------------------------------------------------------*/
+void ri_oracle_ball_query(const float *centers, const float *points, int B, int N, int M, float radius, int U, int *idx)
+{
+    const float r2 = radius * radius;
+    _Pragma("omp parallel for schedule(dynamic)")
+    for (int b = 0; b < B; ++b) {
+        const float *c = centers + (size_t)b * 3 * M;
+        const float *p = points + (size_t)b * 3 * N;
+        int *o = idx + (size_t)b * M * U;
+        for (int j = 0; j < M; ++j) {
+            for (int v = 0; v < U; ++v) o[(size_t)j * U + v] = 0;
+            int cnt = 0;
+            for (int k = 0; k < N && cnt < U; ++k) {
+                float dx = c[j] - p[k], dy = c[j + M] - p[k + N], dz = c[j + 2 * (size_t)M] - p[k + 2 * (size_t)N];
+                float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                if (d2 < r2 && (double)d2 > 1e-5) {
+                    if (cnt == 0)
+                        for (int v = 0; v < U; ++v) o[(size_t)j * U + v] = k;
+                    o[(size_t)j * U + cnt] = k;
+                    ++cnt;
+                }
+            }
+        }
+    }
+}
+
+/* Grouping forward / backward.  PVCNN/modules/functional/src/grouping/grouping.cu:18-44, 58-84.
+ * feat [B,C,N], idx [B,M,U] -> out [B,C,M,U];  grad_x [B,C,N] = scatter-add of grad_y (summed here in index order). */
+void ri_oracle_grouping(const float *feat, const int *idx, int B, int C, int N, int M, int U, float *out)
+{
+    _Pragma("omp parallel for schedule(dynamic)")
+    for (int b = 0; b < B; ++b)
+        for (int l = 0; l < C; ++l)
+            for (size_t e = 0; e < (size_t)M * U; ++e)
+                out[((size_t)b * C + l) * M * U + e] = feat[((size_t)b * C + l) * N + idx[(size_t)b * M * U + e]];
+}
+
+void ri_oracle_grouping_grad(const float *grad_y, const int *idx, int B, int C, int N, int M, int U, float *grad_x)
+{
+    memset(grad_x, 0, (size_t)B * C * N * sizeof(float));
+    _Pragma("omp parallel for schedule(dynamic)")
+    for (int b = 0; b < B; ++b)
+        for (int l = 0; l < C; ++l)
+            for (size_t e = 0; e < (size_t)M * U; ++e)
+                grad_x[((size_t)b * C + l) * N + idx[(size_t)b * M * U + e]] += grad_y[((size_t)b * C + l) * M * U + e];
+}

@@ -40,6 +40,9 @@ SIGNATURES = {
     "ri_sph_trilinear_devox_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "ri_devox_backward_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "ri_voxel_edge_gather_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "ri_ball_query_f32": (_I, [_P, _P, _I, _I, _I, ctypes.c_float, _I, _P, _P]),
+    "ri_grouping_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "ri_grouping_backward_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "ri_mutual_nn_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "ri_mutual_nn_tf32x3": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
 }

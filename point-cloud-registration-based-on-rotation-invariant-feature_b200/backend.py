@@ -6,8 +6,8 @@ src/bindings.cpp:13-56).  This object exposes the SAME function names, positiona
 dtypes and shapes for every hot-path function, so the reference's functional/*.py files run unchanged when
 their `from PVCNN.modules.functional.backend import _backend` resolves to it.
 
-Functions of the reference backend that are outside the hot path (ball_query, grouping, sampling, 3-NN
-interpolation) are not provided here and raise AttributeError.
+ball_query / grouping are served too.  The remaining functions of the reference backend (sampling,
+3-NN interpolation) are outside the path, are not provided here and raise AttributeError.
 """
 import torch
 
@@ -71,6 +71,20 @@ class _Backend:
     @staticmethod
     def spherical_trilinear_devoxelize_backward(grad_y, indices, weights, r):
         return _ri.devox_backward(grad_y, indices, weights, int(r), True)
+
+    # ball_query/ball_query.cpp:6-30 (bindings.cpp name: ball_query)
+    @staticmethod
+    def ball_query(centers_coords, points_coords, radius, num_neighbors):
+        return _ri.ball_query(centers_coords, points_coords, float(radius), int(num_neighbors))
+
+    # grouping/grouping.cpp
+    @staticmethod
+    def grouping_forward(features, indices):
+        return _ri.grouping(features, indices)
+
+    @staticmethod
+    def grouping_backward(grad_y, indices, n):
+        return _ri.grouping_backward(grad_y, indices, int(n))
 
 
 _backend = _Backend()

@@ -3,3 +3,4 @@ from .pvconv import PVConv
 from .shared_mlp import SharedMLP, SE3d
 from .voxelization import Voxelization, Spherical_Voxelization
 from .knn import knnModule
+from .ball_query import BallQuery

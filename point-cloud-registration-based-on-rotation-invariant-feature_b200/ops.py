@@ -405,6 +405,60 @@ def _(xyz, normals, k):
     return xyz.new_empty((B, k, N)), xyz.new_empty((B, k, N), dtype=torch.int32), xyz.new_empty((B, 4, k, N))
 
 
+# ---------------------------------------------------------------------------------- ball query + grouping
+@torch.library.custom_op("ri::ball_query", mutates_args=())
+def ball_query(centers_coords: torch.Tensor, points_coords: torch.Tensor, radius: float, num_neighbors: int) -> torch.Tensor:
+    _req(centers_coords, "centers_coords", torch.float32); _req(points_coords, "points_coords", torch.float32)
+    dev = _same_device(centers_coords, points_coords)
+    B, _, M = centers_coords.shape
+    N = points_coords.shape[2]
+    with torch.cuda.device(dev):
+        out = torch.empty((B, M, num_neighbors), dtype=torch.int32, device=dev)
+        _check(_L.ri_ball_query_f32(centers_coords.data_ptr(), points_coords.data_ptr(), B, N, M, float(radius),
+                                    int(num_neighbors), out.data_ptr(), _stream()), "ri_ball_query")
+    return out
+
+
+@ball_query.register_fake
+def _(centers_coords, points_coords, radius, num_neighbors):
+    return centers_coords.new_empty((centers_coords.shape[0], centers_coords.shape[2], num_neighbors), dtype=torch.int32)
+
+
+@torch.library.custom_op("ri::grouping", mutates_args=())
+def grouping(features: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
+    _req(features, "features", torch.float32); _req(indices, "indices", torch.int32)
+    dev = _same_device(features, indices)
+    B, C, N = features.shape
+    _, M, U = indices.shape
+    with torch.cuda.device(dev):
+        out = torch.empty((B, C, M, U), dtype=torch.float32, device=dev)
+        _check(_L.ri_grouping_f32(features.data_ptr(), indices.data_ptr(), B, C, N, M, U, out.data_ptr(), _stream()),
+               "ri_grouping")
+    return out
+
+
+@grouping.register_fake
+def _(features, indices):
+    return features.new_empty((features.shape[0], features.shape[1], indices.shape[1], indices.shape[2]))
+
+
+@torch.library.custom_op("ri::grouping_backward", mutates_args=())
+def grouping_backward(grad_y: torch.Tensor, indices: torch.Tensor, n: int) -> torch.Tensor:
+    _req(grad_y, "grad_y", torch.float32); _req(indices, "indices", torch.int32)
+    dev = _same_device(grad_y, indices)
+    B, C, M, U = grad_y.shape
+    with torch.cuda.device(dev):
+        gx = torch.empty((B, C, n), dtype=torch.float32, device=dev)
+        _check(_L.ri_grouping_backward_f32(grad_y.data_ptr(), indices.data_ptr(), B, C, n, M, U, gx.data_ptr(), _stream()),
+               "ri_grouping_backward")
+    return gx
+
+
+@grouping_backward.register_fake
+def _(grad_y, indices, n):
+    return grad_y.new_empty((grad_y.shape[0], grad_y.shape[1], n))
+
+
 # ---------------------------------------------------------------------------------------------- matcher
 @torch.library.custom_op("ri::mutual_nn", mutates_args=())
 def mutual_nn(desc1: torch.Tensor, desc2: torch.Tensor, point_major: bool) -> tuple[

@@ -83,3 +83,37 @@ def test_cube(oracle, golden_dir, r):
     assert np.array_equal(di, g[f"r{r}_dinds"]) and np.array_equal(dw, g[f"r{r}_dwgts"])
     assert np.array_equal(o, g[f"r{r}_douts"])
     assert scaled_err(oracle.devox_grad(g[f"r{r}_dgy"], di, dw, r, False), g[f"r{r}_dgx"]) <= TOL
+
+
+def test_ball_query_oracle_properties(oracle):
+    """ball query restatement: first-U-in-index-order, self and near-duplicates excluded, first hit fills the row."""
+    g = np.random.default_rng(1)
+    pts = (g.standard_normal((2, 3, 300)) * 0.3).astype(np.float32)
+    idx = oracle.ball_query(pts, pts, 0.3, 16)
+    x = pts.astype(np.float64)
+    d2 = ((x[:, :, :, None] - x[:, :, None, :]) ** 2).sum(1)
+    for b in range(2):
+        for j in range(0, 300, 37):
+            nb = np.nonzero((d2[b, j] < np.float32(0.3) ** 2 * (1 - 1e-6)) & (d2[b, j] > 1.01e-5))[0]
+            row = idx[b, j]
+            assert j not in row or len(nb) == 0
+            k = min(len(nb), 16)
+            assert np.array_equal(row[:k], nb[:k])
+            if 0 < k < 16:
+                assert (row[k:] == nb[0]).all()
+            if k == 0:
+                assert (row == 0).all()
+    f = g.standard_normal((2, 4, 300)).astype(np.float32)
+    grp = oracle.grouping(f, idx)
+    assert np.array_equal(grp[1, 2], f[1, 2][idx[1]])
+
+
+def test_ball_query_golden(oracle, golden_dir):
+    from _util import load_golden
+    g = load_golden(golden_dir, "ball_query.npz")
+    for name in "abc":
+        idx = oracle.ball_query(g["centers"], g["points"], float(g[name + "_radius"]), int(g[name + "_u"]))
+        assert np.array_equal(idx, g[name + "_idx"])
+        assert np.array_equal(oracle.grouping(g[name + "_feat"], idx), g[name + "_grp"])
+        gx = oracle.grouping_grad(g[name + "_gy"], idx, g["points"].shape[2])
+        assert np.abs(gx - g[name + "_gx"]).max() <= 1e-5 * np.abs(g[name + "_gx"]).max()

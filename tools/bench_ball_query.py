@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Ball query + grouping at the shipped models' shape — B=32, N=M=1024, radius 0.3, u=128, grouping of
+64-channel features ([B,64,1024,128] = 1.07 GB) — next to the reference's own kernels (oracle/_ref) on the same GPU."""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ri_b200
+from ri_b200 import synth
+B, N, U, C, R = 32, 1024, 128, 64, 0.3
+pts = torch.from_numpy(np.ascontiguousarray(synth.make_clouds(B, N, seed=1)[:, :3])).cuda()
+feat = torch.randn(B, C, N, device="cuda")
+
+def t(fn, reps=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+idx = torch.ops.ri.ball_query(pts, pts, R, U)
+a = t(lambda: torch.ops.ri.ball_query(pts, pts, R, U))
+b = t(lambda: torch.ops.ri.grouping(feat, idx))
+out_bytes = B * C * N * U * 4
+print("ours     : ball_query %8.1f us   grouping %8.1f us (%.0f GB/s of output written)" % (a, b, out_bytes / b / 1e3))
+try:
+    from oracle.build_ref import load_ref
+    ref = load_ref()
+    ra = t(lambda: ref.ball_query(pts, pts, R, U), 5)
+    rb = t(lambda: ref.grouping_forward(feat, idx), 5)
+    print("reference: ball_query %8.1f us   grouping %8.1f us   -> %.0fx / %.0fx" % (ra, rb, ra / a, rb / b))
+    assert torch.equal(ref.ball_query(pts, pts, R, U), idx)
+except Exception as ex:
+    print("reference backend unavailable:", ex)
