@@ -47,6 +47,11 @@ WORKLOADS = {
                    name="sph_dg front end: 32 x 1024 pts with normals, k=20 KNN+PPF, spherical voxelize r=32 C=67, "
                         "spherical trilinear devox, DGCNN edge gather (BASELINE configs[0])"),
 }
+# BASELINE.json configs[4]: throughput sweep over the spherical resolution (4096 clouds x 1024 pts = 128 steps of 32 clouds)
+for _r in (16, 64):
+    WORKLOADS["sph_r%d" % _r] = dict(voxel_shape="spherical", B=32, N=1024, C=67, k=20, r=_r,
+                                     name="sph_dg front end at spherical res %d: 32 x 1024 pts per step, k=20 KNN+PPF, C=67 "
+                                          "(BASELINE configs[4] sweep)" % _r)
 RING = 3          # independent input/output buffer sets cycled between timed steps (footprint > L2)
 
 
