@@ -17,7 +17,7 @@ from . import _lib            # noqa: F401  raises ImportError when libri_b200.s
 from . import ops             # noqa: F401  registers torch.ops.ri.*
 from .backend import _backend  # noqa: F401
 from . import functional, modules  # noqa: F401
-from .frontend import FrontEnd, FrontEndPipeline  # noqa: F401
+from .frontend import FrontEnd, FrontEndLanes, FrontEndPipeline  # noqa: F401
 from . import shard, synth, matcher  # noqa: F401
 
 __version__ = '0.1.0'

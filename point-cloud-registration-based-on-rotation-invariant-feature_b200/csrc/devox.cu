@@ -104,6 +104,252 @@ devox_kernel(const float* __restrict__ coords, const float* __restrict__ feat, c
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming cube devoxelizer.  At r = 32, N = 1024 the 8 corners of a cloud's points touch about every 32-byte sector
+// of a 128 KB channel plane, so the gather form above effectively reads the whole grid through L1 as a miss buffer —
+// its speed follows the L1 size, which forces it into a different L1/shared-memory split from the rest of the step
+// (ri_common.cuh, carveout note).  This form reads the grid the way the grid writer writes it: a persistent CTA per
+// SM streams x-slab ranges of its planes into a shared-memory ring with cp.async.bulk (TMA engine, mbarrier
+// complete_tx) and the points gather their corners from shared memory.  No L1 dependence, one carveout family for
+// the whole step, reads are sequential 64 KB bursts, every grid byte is read exactly once.
+//
+//   work unit  plane (cloud b, channel c); every CTA owns a contiguous range of planes, so it meets at most a few
+//              clouds and computes a cloud's corner data (base corner, 3 high-offset bits, 8 weights per point, in
+//              registers) once per cloud;
+//   tile       TS consecutive x-slabs of a plane, NO halo: the reference's 8-term chain visits the four low-x corners
+//              first (001 mul, fma 000, 010, 011) and the four high-x corners after (100, 101, 110, 111), so a point adds
+//              its low half when the tile holding slab floor(x) passes and continues the same chain with its high half
+//              when the tile holding slab floor(x)+1 passes (the same tile or the next one) — the accumulator lives
+//              in a register across tiles, the order of operations is untouched: bit-identical to devox_kernel;
+//   warps      8 consumer warps (P = ceil(N/256) points per thread) + 1 producer warp; full[] barriers carry the TMA
+//              byte counts, empty[] barriers get one arrival per consumer warp, so warps drift freely and the
+//              producer refills a slot as soon as the last warp has left it.
+constexpr int kSdThreads = 256;                     // consumer threads
+constexpr int kSdWarps = kSdThreads / 32;
+constexpr int kSdMaxRing = 8;
+constexpr uint32_t kSdTileBytesDefault = 64u << 10;   // measured: 8 / 16 / 32 / 64 KB tiles -> 154 / 91 / 58 / 56 us (B200, 32 x 71 planes)
+constexpr uint32_t kSdRingBytesDefault = 128u << 10;   // leaves room for k-NN CTAs on the same SM
+
+__device__ __forceinline__ void sd_mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sd_mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sd_mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void sd_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sd_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int P>
+__global__ void __launch_bounds__(kSdThreads + 32, 1)
+devox_stream_kernel(const float* __restrict__ coords, const float* __restrict__ feat, int B, int C, int N, int r,
+                    int TS, int nt, uint32_t slot_bytes, int R,
+                    float* __restrict__ outs, int* __restrict__ inds, float* __restrict__ wgts)
+{
+    extern __shared__ __align__(128) unsigned char sd_smem[];
+    __shared__ __align__(8) uint64_t full[kSdMaxRing];
+    __shared__ __align__(8) uint64_t empty[kSdMaxRing];
+    const int tid = threadIdx.x;
+    const int r2 = r * r;
+    const size_t s = (size_t)r2 * r;
+    const long long planes = (long long)B * C;
+    // contiguous, balanced plane range of this CTA
+    const int p0 = (int)(planes * blockIdx.x / gridDim.x), p1 = (int)(planes * (blockIdx.x + 1) / gridDim.x);
+    const int my_tiles = (p1 - p0) * nt;
+
+    if (tid == 0) {
+        for (int i = 0; i < R; ++i) { sd_mbar_init(ri_smem_u32(&full[i]), 1); sd_mbar_init(ri_smem_u32(&empty[i]), kSdWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= kSdThreads) {
+        // ---------------------------------------------------------------- producer warp (one lane issues)
+        if (tid == kSdThreads) {
+            int slot = 0; uint32_t round = 0;
+            for (int n = 0; n < my_tiles; ++n) {
+                const int pl = p0 + n / nt, t = n - (n / nt) * nt;
+                const int x0 = t * TS;
+                const int nsl = min(r, x0 + TS) - x0;
+                const uint32_t bytes = (uint32_t)nsl * (uint32_t)r2 * 4u;
+                const float* src = feat + (size_t)pl * s + (size_t)x0 * r2;
+                if (round > 0) sd_mbar_wait(ri_smem_u32(&empty[slot]), (round - 1) & 1);
+                const uint32_t bar = ri_smem_u32(&full[slot]);
+                sd_mbar_expect_tx(bar, bytes);
+                sd_bulk_g2s(ri_smem_u32(sd_smem + (size_t)slot * slot_bytes), src, bytes, bar);
+                if (++slot == R) { slot = 0; ++round; }
+            }
+        }
+        return;
+    }
+
+    // -------------------------------------------------------------------- consumers
+    const int lane = tid & 31;
+    int id0[P], tl[P];          // id0: base corner | high-offset bits << 28;  tl: tile of the low half | tile of the high half << 8
+    float w[P][8];
+    int cur_b = -1;
+    int slot = 0; uint32_t round = 0;
+    for (int pl = p0; pl < p1; ++pl) {
+        const int b = pl / C, c = pl - b * C;
+        if (b != cur_b) {
+            cur_b = b;
+            const float* X = coords + (size_t)b * 3 * N;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const int i = tid + p * kSdThreads;
+                tl[p] = 0xffff;                    // no point: matches no tile
+                id0[p] = 0;
+                if (i < N) {
+                    const float x = X[i], y = X[i + N], z = X[i + 2 * (size_t)N];
+                    const float xl = floorf(x), yl = floorf(y), zl = floorf(z);
+                    int id[8];
+                    ri_corners(__fsub_rn(x, xl), __fsub_rn(y, yl), __fsub_rn(z, zl), (int)xl, (int)yl, (int)zl, r, r2, id, w[p]);
+                    const int hbits = (id[1] != id[0] ? 1 : 0) | (id[2] != id[0] ? 2 : 0) | (id[4] != id[0] ? 4 : 0);
+                    const int xi = (int)xl, yi = (int)yl, zi = (int)zl;
+                    const int xh = xi + ((hbits >> 2) & 1);
+                    const bool inside = xi >= 0 && yi >= 0 && zi >= 0 && xh < r &&
+                                        yi + ((hbits >> 1) & 1) < r && zi + (hbits & 1) < r;
+                    tl[p] = inside ? ((xi / TS) | ((xh / TS) << 8)) : 0xfefe;   // 0xfefe: outside the grid, global path
+                    id0[p] = id[0] | (hbits << 28);
+                }
+            }
+        }
+        if (c == 0) {
+            // the CTA that owns a cloud's first plane also emits inds / wgts
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const int i = tid + p * kSdThreads;
+                if (i < N) {
+                    const int base = id0[p] & 0x0fffffff;
+                    const int hc = (id0[p] >> 28) & 1, hb = ((id0[p] >> 29) & 1) * r, ha = ((id0[p] >> 30) & 1) * r2;
+                    int* I = inds + (size_t)b * 8 * N + i;
+                    float* Wt = wgts + (size_t)b * 8 * N + i;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        I[(size_t)u * N] = base + ((u & 1) ? hc : 0) + ((u & 2) ? hb : 0) + ((u & 4) ? ha : 0);
+                        Wt[(size_t)u * N] = w[p][u];
+                    }
+                }
+            }
+        }
+        float acc[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) acc[p] = 0.f;
+        for (int t = 0; t < nt; ++t) {
+            sd_mbar_wait(ri_smem_u32(&full[slot]), round & 1);
+            const float* tile = reinterpret_cast<const float*>(sd_smem + (size_t)slot * slot_bytes);
+            const int tile_base = t * TS * r2;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const int base = (id0[p] & 0x0fffffff) - tile_base;
+                const int hc = (id0[p] >> 28) & 1, hb = ((id0[p] >> 29) & 1) * r, ha = ((id0[p] >> 30) & 1) * r2;
+                if ((tl[p] & 0xff) == t) {
+                    const float* f = tile + base;
+                    float a = __fmul_rn(w[p][1], f[hc]);
+                    a = __fmaf_rn(w[p][0], f[0], a);
+                    a = __fmaf_rn(w[p][2], f[hb], a);
+                    acc[p] = __fmaf_rn(w[p][3], f[hb + hc], a);
+                }
+                if ((tl[p] >> 8) == t) {
+                    const float* f = tile + base + ha;
+                    float a = __fmaf_rn(w[p][4], f[0], acc[p]);
+                    a = __fmaf_rn(w[p][5], f[hc], a);
+                    a = __fmaf_rn(w[p][6], f[hb], a);
+                    acc[p] = __fmaf_rn(w[p][7], f[hb + hc], a);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) sd_mbar_arrive(ri_smem_u32(&empty[slot]));
+            if (++slot == R) { slot = 0; ++round; }
+        }
+        const float* F = feat + (size_t)pl * s;
+        float* O = outs + (size_t)pl * N;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const int i = tid + p * kSdThreads;
+            if (tl[p] == 0xfefe) {                             // outside the grid: what the gather form would read
+                const int base = id0[p] & 0x0fffffff;
+                int id[8]; float ww[8];
+                const int hc = (id0[p] >> 28) & 1, hb = ((id0[p] >> 29) & 1) * r, ha = ((id0[p] >> 30) & 1) * r2;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    long long v = (long long)base + ((u & 1) ? hc : 0) + ((u & 2) ? hb : 0) + ((u & 4) ? ha : 0);
+                    v = v < 0 ? 0 : (v >= (long long)s ? (long long)s - 1 : v);
+                    id[u] = (int)v; ww[u] = w[p][u];
+                }
+                acc[p] = devox_sum(F, id, ww);
+            }
+            if (i < N) O[i] = acc[p];
+        }
+    }
+}
+
+// host-side geometry of the streaming form; returns false when it does not apply
+struct SdPlan { int TS, nt, R; uint32_t slot_bytes; };
+static bool sd_plan(const float* feat, int C, int N, int r, SdPlan& pl)
+{
+    // RI_DEVOX_STREAM=0 forces the gather form, =1 takes the streaming form wherever it is able to run (tests compare
+    // the two); unset: streaming where a whole plane is not much more than what the gathers would move
+    const char* ev = getenv("RI_DEVOX_STREAM");
+    const int mode = ev ? atoi(ev) + 1 : 0;
+    if (mode == 1) return false;
+    if (C < 1 || N < 1 || N > kSdThreads * 8 || (r & 1) || r < 2) return false;
+    if (((uintptr_t)feat & 15) != 0) return false;
+    const size_t slab = (size_t)r * r * 4, plane = slab * r;
+    uint32_t tile_bytes = kSdTileBytesDefault, ring_bytes = kSdRingBytesDefault;
+    if (const char* e2 = getenv("RI_DEVOX_TILE_KB")) { const int v = atoi(e2); if (v >= 1 && v <= 96) tile_bytes = (uint32_t)v << 10; }
+    if (const char* e3 = getenv("RI_DEVOX_RING_KB")) { const int v = atoi(e3); if (v >= 2 && v <= 208) ring_bytes = (uint32_t)v << 10; }
+    if (slab > tile_bytes) return false;
+    if (plane / 4 >= (1u << 28)) return false;      // base index is packed into 28 bits
+    // the gather form moves ~128 B per point and plane; stream only where a whole plane is not much more than that
+    if (mode != 2 && plane > (size_t)256 * N) return false;
+    int TS = (int)(tile_bytes / slab);
+    if (TS > r) TS = r;
+    pl.TS = TS;
+    pl.nt = (r + TS - 1) / TS;
+    if (pl.nt > 250) return false;                  // tile numbers are packed into 8 bits
+    pl.slot_bytes = (uint32_t)((TS * slab + 127) & ~(size_t)127);
+    int R = (int)(ring_bytes / pl.slot_bytes);
+    pl.R = R > kSdMaxRing ? kSdMaxRing : R;
+    return pl.R >= 2;
+}
+
+template <int P>
+static int sd_launch(const SdPlan& pl, const float* coords, const float* feat, int B, int C, int N, int r,
+                     float* outs, int* inds, float* wgts, cudaStream_t st)
+{
+    auto kern = devox_stream_kernel<P>;
+    const size_t smem = (size_t)pl.R * pl.slot_bytes;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    ri_prefer_step_carveout(kern);
+    const long long planes = (long long)B * C;
+    const int grid = planes < ri_num_sms() ? (int)planes : ri_num_sms();
+    kern<<<grid, kSdThreads + 32, smem, st>>>(coords, feat, B, C, N, r, pl.TS, pl.nt, pl.slot_bytes, pl.R, outs, inds, wgts);
+    RI_LAUNCH_CHECK();
+    return RI_OK;
+}
+
 // out[b, c, i]     = inds[b,i] == -1 ? 0 : feat[b,c,i] - avg[b,c,inds[b,i]]
 // out[b, C + c, i] = feat[b,c,i]                                                    (pvconv.py:68-90)
 constexpr int kEdgeThreads = 128;
@@ -145,6 +391,14 @@ int devox_impl(const float* coords, const float* feat, const int* g_inds, int B,
     if (B < 0 || C < 0 || N < 0 || r <= 0 || r > 1024) return RI_ERR_BAD_ARG;
     if ((long long)r * r * r > 0x7fffffffLL || B > 65535) return RI_ERR_UNSUPPORTED;
     if (B == 0 || N == 0) return RI_OK;
+    if (!SPH) {
+        SdPlan pl;
+        if ((long long)B * C < 0x7fffffffLL && sd_plan(feat, C, N, r, pl)) {
+            const int P = (N + kSdThreads - 1) / kSdThreads;
+            if (P <= 4) return sd_launch<4>(pl, coords, feat, B, C, N, r, outs, inds, wgts, st);
+            return sd_launch<8>(pl, coords, feat, B, C, N, r, outs, inds, wgts, st);
+        }
+    }
     const int groups = C > 0 ? (C + kDevoxChans - 1) / kDevoxChans : 1;   // one group still writes inds/wgts
     dim3 grid((N + kDevoxThreads - 1) / kDevoxThreads, groups, B);
     devox_kernel<SPH><<<grid, kDevoxThreads, 0, st>>>(coords, feat, g_inds, C, N, r, outs, inds, wgts);

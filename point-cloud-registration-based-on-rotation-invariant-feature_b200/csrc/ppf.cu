@@ -166,6 +166,14 @@ extern "C" int ri_ppf_gather_packed_f32(const float* packed, const int* idx, int
     if (B == 0 || N == 0) return RI_OK;
     const size_t kN = (size_t)k * N;
     dim3 grid((unsigned)((kN + kGatherThreads - 1) / kGatherThreads), B);
+    // no shared memory, but the carveout PREFERENCE still decides which kernels an SM can host at the same time: ask for
+    // the step's split so it runs next to the streaming devoxelizer / grid writer / k-NN (RI_PPF_MAXL1=1: the default split)
+    static int carveout_set = 0;
+    if (!carveout_set) {
+        const char* ev = getenv("RI_PPF_MAXL1");
+        if (!(ev && atoi(ev) == 1)) ri_prefer_step_carveout(ppf_gather_packed_kernel);
+        carveout_set = 1;
+    }
     ppf_gather_packed_kernel<<<grid, kGatherThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(packed), idx, N, k, out);
     RI_LAUNCH_CHECK();
     return RI_OK;

@@ -37,7 +37,7 @@ class FrontEnd:
 
     def __init__(self, B, N, C, k=20, r=32, voxel_shape='spherical', normalize=False, eps=0.0,
                  device='cuda', use_graph=True, overlap=True, grid_chunks=None, devox_side_stream=True,
-                 knn_after_front=True, join_before_devox=True):
+                 knn_after_front=True, join_before_devox=None):
         if voxel_shape not in ('spherical', 'cube'):
             raise ValueError('voxel_shape must be "spherical" or "cube"')
         self.B, self.N, self.C, self.k, self.r = int(B), int(N), int(C), int(k), int(r)
@@ -60,6 +60,12 @@ class FrontEnd:
             grid_chunks = 1
         self.grid_chunks = int(max(1, min(grid_chunks, max(B, 1))))
         self.devox_side_stream = bool(devox_side_stream)
+        if join_before_devox is None:
+            # The cube devoxelizer streams the grid through shared memory (devox.cu, streaming form) and belongs to the same
+            # L1/shared-memory split as the k-NN and the grid writer, so it starts as soon as the grid is written
+            # (measured step 192 -> 179 us).  The spherical one is the gather form, which wants the max-L1 split and so
+            # runs after the k-NN has left the SMs.
+            join_before_devox = voxel_shape != 'cube' or N > 2048 or r % 2 != 0 or 4 * r ** 3 > 256 * N
         self.knn_after_front, self.join_before_devox = bool(knn_after_front), bool(join_before_devox)
         nb = -(-B // self.grid_chunks)
         self._chunks = [(b0, min(B, b0 + nb)) for b0 in range(0, B, nb)]
@@ -150,11 +156,13 @@ class FrontEnd:
                 self._side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(self._side):
                     self._knn()
+                    if join is None:
+                        self._ppf()            # one carveout family: the side branch simply runs to its end
             _check(_L.ri_voxelize_fill_f32(B, C, N, r, 0, B, self.grid.data_ptr(), self.cnt.data_ptr(),
                                            self._ws.data_ptr(), self._ws_bytes, st), 'ri_voxelize_fill')
             if join is not None:
                 torch.cuda.current_stream().wait_stream(join)      # see below: the devoxelizer runs after the k-NN
-            if fork is not None:
+            if fork is not None and join is not None:
                 # PPF (no shared memory, fp64-ALU bound) next to the devoxelizer (gather bound): both run with the
                 # default max-L1 carveout, so they share the SMs once the max-shared kernels are gone
                 self._side.wait_stream(torch.cuda.current_stream())
@@ -295,6 +303,51 @@ class FrontEnd:
         edge = 4 * N + 4 * C * N + 4 * C * N + 8 * C * N
         return {'knn_ppf': B * knn_ppf, 'voxelize': B * vox, 'devox': B * devox, 'edge': B * edge,
                 'total': B * (knn_ppf + vox + devox + edge)}
+
+
+class FrontEndLanes:
+    """Keeps several steps in flight on the device: step i runs engine i % len(engines) on launch stream i % lanes.
+    Consecutive steps are independent batches, so the latency-bound prefix of step i+1 (mean, cell sort, cell means) and its
+    ALU-bound k-NN run under the HBM-bound grid write / devoxelize of step i.  An engine is never replayed before its own
+    previous step has finished (per-engine event).
+
+        lanes = FrontEndLanes(engines, lanes=2)
+        lanes.begin()                 # the launch streams pick up after the current stream
+        for i in range(K): lanes.forward(i)
+        lanes.end()                   # the current stream waits for every step in flight
+    """
+
+    def __init__(self, engines, lanes=2):
+        self.engines = list(engines)
+        self.device = self.engines[0].device
+        self.lanes = int(lanes)
+        with torch.cuda.device(self.device):
+            self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.lanes)]
+            self._done = [None] * len(self.engines)
+            for fe in self.engines:                # graphs are captured up front: a capture cannot overlap other work
+                fe.forward()
+            torch.cuda.synchronize(self.device)
+
+    def begin(self):
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+
+    def forward(self, i):
+        e = i % len(self.engines)
+        lane = self.streams[i % self.lanes]
+        if self._done[e] is not None:
+            lane.wait_event(self._done[e])
+        with torch.cuda.stream(lane):
+            self.engines[e].forward()
+            ev = self._done[e] if self._done[e] is not None else torch.cuda.Event()
+            ev.record(lane)
+            self._done[e] = ev
+
+    def end(self):
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)
 
 
 class FrontEndPipeline:

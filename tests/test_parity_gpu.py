@@ -223,6 +223,40 @@ def test_sph_voxelize_vs_reference(ri, ref_backend, oracle, B, N, C, r):
             assert np.array_equal(A(out), omean)      # tiled path sums in point order, exactly like the oracle
 
 
+@pytest.mark.parametrize("B,N,C,r", [(32, 1024, 71, 32), (3, 1000, 5, 16), (2, 2048, 3, 32), (2, 1500, 4, 32), (5, 257, 2, 8),
+                                      (1, 64, 150, 32), (2, 300, 3, 2), (2, 1024, 3, 64), (3, 1024, 7, 22)])
+def test_cube_devox_streaming_vs_gather_vs_oracle(ri, oracle, B, N, C, r):
+    """The two forms of the cube devoxelizer (TMA-streamed planes + shared-memory gathers; per-thread global gathers) and the C
+    oracle agree bit for bit on outs / inds / wgts — including points on cell boundaries, on the far faces (x = r-1: no
+    high corner) and at the grid's corners."""
+    import os
+    g = torch.Generator().manual_seed(100 + r + N)
+    nc = torch.rand(B, 3, N, generator=g) * (r - 1)
+    nc[:, :, :N // 8] = torch.round(nc[:, :, :N // 8])                  # integer coordinates: zero high weights
+    nc[:, 0, N // 8:N // 6] = r - 1                                     # far x face
+    nc[:, :, N // 6:N // 5] = torch.randint(0, 2, (B, 3, N // 5 - N // 6), generator=g).float() * (r - 1)   # corners
+    nc = nc.cuda().contiguous()
+    grid = torch.randn(B, C, r, r, r, generator=g).cuda()
+    res = {}
+    prev = os.environ.get("RI_DEVOX_STREAM")
+    try:
+        for mode in ("0", "1"):
+            os.environ["RI_DEVOX_STREAM"] = mode
+            res[mode] = torch.ops.ri.trilinear_devox(nc, grid, r)
+            torch.cuda.synchronize()
+    finally:
+        if prev is None:
+            os.environ.pop("RI_DEVOX_STREAM", None)
+        else:
+            os.environ["RI_DEVOX_STREAM"] = prev
+    oo, oi, ow = oracle.trilinear_devoxelize(A(nc), A(grid), r)
+    for mode in ("0", "1"):
+        o, di, dw = res[mode]
+        assert np.array_equal(A(di), oi), "corner indices, form %s" % mode
+        assert np.array_equal(A(dw), ow), "corner weights, form %s" % mode
+        assert np.array_equal(A(o), oo), "devoxelized features, form %s" % mode
+
+
 @pytest.mark.parametrize("B,N,C,r", [(32, 1024, 71, 32), (4, 900, 6, 16), (2, 5000, 3, 32)])
 def test_cube_pipeline_vs_reference(ri, ref_backend, oracle, B, N, C, r):
     pts = clouds(B, N, 21)
