@@ -207,6 +207,38 @@ int ri_mutual_nn_tf32x3(const float* desc1, const float* desc2, int P, int C, in
                         int* corr12, int* corr21, float* dist12, int* idx1, int* idx2, int* count,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- barycentre grid subsampling ---------------------------------------------------------------
+ * grid_subsampling() (cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.cpp:4-106, called through
+ * cpp_subsampling/wrapper.cpp:58-285 and utils/grid_subsampleing.py:3-21): one barycentre per occupied cell of edge dl.
+ * points [N,3] row-major (the reference's numpy layout), features [N,fdim] or NULL, labels [N,ldim] or NULL ->
+ * out_points [<=N,3], out_features [<=N,fdim], out_labels [<=N,ldim] (allocate for N cells), *out_count = number of cells
+ * (DEVICE memory; no host synchronisation inside).  Cells come out in ascending cell index (the reference's order is an
+ * unordered_map's); sums run in original point order, so barycentres and features are bit-identical to the reference;
+ * label ties go to the smallest label.  workspace >= ri_grid_subsample_workspace_bytes(N). */
+size_t ri_grid_subsample_workspace_bytes(int N);
+int ri_grid_subsample_f32(const float* points, const float* features, const int* labels, int N, int fdim, int ldim,
+                          float dl, float* out_points, float* out_features, int* out_labels, int* out_count,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- correspondences -> rigid pose -> registration metrics --------------------------------------
+ * What follows the matcher in the reference's meter (datasets/deepgmr_mn40.py:104-139): the solve is delegated there to
+ * Open3D RANSAC / FGR (utils/open3d_func.py:34-75) or TEASER++ (deepgmr_mn40.py:175-230) on the host, one pair at a time.
+ * Here: RANSAC over the mutual matches with the configuration the reference hands to Open3D (3-point samples,
+ * edge-length similarity 0.9, sample residual and validation distance = voxel_size, max_iter hypotheses, point-to-point
+ * least squares without scale), all pairs in one launch, then Horn's closed-form refit on the inliers.
+ * src [P,n1,3], tgt [P,n2,3] point-major fp32; idx1, idx2 [P,ld], count [P] as ri_mutual_nn_tf32x3 returns them;
+ * hyps == 0: least squares over all matches (Kabsch).  T [P,4,4] row-major fp32 (src -> tgt), inliers [P];
+ * best: P * 8 bytes of scratch (may be NULL when hyps == 0). */
+int ri_pose_from_matches_f32(const float* src, const float* tgt, const int* idx1, const int* idx2, const int* count,
+                             int P, int n1, int n2, int ld, int hyps, float inlier_dist, float edge_similarity,
+                             int refine_iters, unsigned long long seed, float* T, int* inliers,
+                             unsigned long long* best, void* stream);
+
+/* RE_TE_one_pair (deepgmr_mn40.py:152-164) + the point RMSE of MeterModelNet40_registration.update (:121-126), fp64:
+ * gt, est [P,4,4] row-major fp32, pts [P,n,3] -> out [P,3] double = (rotation error in degrees, translation error, rmse). */
+int ri_registration_metrics_f32(const float* gt, const float* est, const float* pts, int P, int n, double* out,
+                                void* stream);
+
 #ifdef __cplusplus
 }
 #endif

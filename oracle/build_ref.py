@@ -61,6 +61,51 @@ def build(force=False, verbose=False):
     return so_path()
 
 
+GRIDSUB_DIR = "/root/reference/cpp_wrappers/cpp_subsampling"
+GRIDSUB_SO = os.path.join(OUT_DIR, "libgridsub_ref.so")
+
+
+def build_gridsub(force=False):
+    """The reference's CPU grid subsampling (cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.cpp +
+    cpp_utils/cloud/cloud.cpp, compiled where they lie with the flags of cpp_subsampling/setup.py) behind the C shim
+    oracle/gridsub_ref_shim.cpp -> oracle/_ref/libgridsub_ref.so.  Returns the path, or None when the reference tree is
+    absent and no prebuilt file exists."""
+    if not os.path.isdir(GRIDSUB_DIR):
+        return GRIDSUB_SO if os.path.exists(GRIDSUB_SO) else None
+    if os.path.exists(GRIDSUB_SO) and not force:
+        return GRIDSUB_SO
+    import subprocess
+    os.makedirs(OUT_DIR, exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++11", "-fPIC", "-shared", "-I", GRIDSUB_DIR,
+                           os.path.join(HERE, "gridsub_ref_shim.cpp"),
+                           os.path.join(GRIDSUB_DIR, "grid_subsampling", "grid_subsampling.cpp"),
+                           os.path.join(GRIDSUB_DIR, "..", "cpp_utils", "cloud", "cloud.cpp"),
+                           "-o", GRIDSUB_SO])
+    return GRIDSUB_SO
+
+
+def ref_grid_subsampling(points, features=None, labels=None, grid_size=0.1):
+    """Run the reference's own grid_subsampling() (unordered_map output order).  numpy in / out; None if unavailable."""
+    import ctypes
+    import numpy as np
+    p = build_gridsub()
+    if p is None:
+        return None
+    lib = ctypes.CDLL(p)
+    pts = np.ascontiguousarray(points, np.float32)
+    N = pts.shape[0]
+    f = None if features is None else np.ascontiguousarray(features, np.float32).reshape(N, -1)
+    l = None if labels is None else np.ascontiguousarray(labels, np.int32).reshape(N, -1)
+    fdim = 0 if f is None else f.shape[1]
+    ldim = 0 if l is None else l.shape[1]
+    op = np.empty((N, 3), np.float32); of = np.empty((N, max(fdim, 1)), np.float32); ol = np.empty((N, max(ldim, 1)), np.int32)
+    vp = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+    lib.ref_grid_subsampling.restype = ctypes.c_int
+    lib.ref_grid_subsampling.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_float] + [ctypes.c_void_p] * 3
+    M = lib.ref_grid_subsampling(vp(pts), vp(f), vp(l), N, fdim, ldim, float(grid_size), vp(op), vp(of), vp(ol))
+    return op[:M], (of[:M, :fdim] if fdim else None), (ol[:M, :ldim] if ldim else None)
+
+
 def load_ref():
     """Import the prebuilt reference backend (needs `import torch` first). Returns module or None."""
     p = so_path()
@@ -77,3 +122,4 @@ def load_ref():
 if __name__ == "__main__":
     p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print("reference backend:", p)
+    print("reference grid subsampling:", build_gridsub(force="--force" in sys.argv))

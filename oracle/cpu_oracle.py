@@ -260,3 +260,70 @@ def voxelization_module(features, coords, r, normalize=True, eps=0.0):
     vox = np.rint(nc).astype(np.int32)                     # torch.round == half-to-even == rint
     out, ind, _ = avg_voxelize(features, vox, r)
     return out, ind, nc
+
+
+def grid_subsample(points, features=None, labels=None, grid_size=0.1):
+    """utils/grid_subsampleing.py:3-21 -> cpp_subsampling grid_subsampling.cpp:4-106.  points (N,3), features (N,d),
+    labels (N,) or (N,l) -> (sub_points, sub_features, sub_labels, cell_keys), cells in ascending cell index."""
+    pts = _f(points)
+    N = pts.shape[0]
+    f = None if features is None else _f(features).reshape(N, -1)
+    l = None if labels is None else _i(labels).reshape(N, -1)
+    fdim = 0 if f is None else f.shape[1]
+    ldim = 0 if l is None else l.shape[1]
+    op = np.empty((max(N, 1), 3), np.float32); of = np.empty((max(N, 1), max(fdim, 1)), np.float32)
+    ol = np.empty((max(N, 1), max(ldim, 1)), np.int32); keys = np.empty(max(N, 1), np.uint64)
+    fn = lib().ri_oracle_grid_subsample
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_float] + [ctypes.c_void_p] * 4
+    M = fn(_p(pts), None if f is None else _p(f), None if l is None else _p(l), N, fdim, ldim, float(grid_size),
+           _p(op), _p(of), _p(ol), _p(keys))
+    return op[:M].copy(), (of[:M, :fdim].copy() if fdim else None), (ol[:M, :ldim].copy() if ldim else None), keys[:M].copy()
+
+
+# ---------------------------------------------------------------------------------------------- registration (row f3)
+def re_te_one_pair(gt, est):
+    """RE_TE_one_pair, datasets/deepgmr_mn40.py:152-164 (numpy, as the reference): rotation error in degrees, |dt|."""
+    import math
+    gt_R = gt[:3, :3]
+    est_R = est[:3, :3]
+    A = (np.trace(np.dot(gt_R.T, est_R)) - 1) / 2
+    if A > 1:
+        A = 1
+    elif A < -1:
+        A = -1
+    return math.degrees(math.fabs(math.acos(A))), np.linalg.norm(gt[:3, 3] - est[:3, 3])
+
+
+def apply_transform_2dim_numpy(pts, trans):
+    """utils/open3d_func.py:104-110."""
+    return pts.dot(trans[:3, :3].T) + trans[:3, 3][np.newaxis, :]
+
+
+def registration_metrics(gt, est, pts):
+    """Per pair (rre, rte, rmse) as MeterModelNet40_registration.update computes them (deepgmr_mn40.py:119-126).
+    gt, est [P,4,4], pts [P,n,3] -> [P,3] float64."""
+    out = np.zeros((len(gt), 3))
+    for i in range(len(gt)):
+        rre, rte = re_te_one_pair(gt[i], est[i])
+        d = apply_transform_2dim_numpy(pts[i], est[i]) - apply_transform_2dim_numpy(pts[i], gt[i])
+        out[i] = (rre, rte, np.mean(np.linalg.norm(d, axis=1)))
+    return out
+
+
+def kabsch(a, b):
+    """Least-squares rigid transform mapping a [m,3] onto b [m,3] (rotation + translation, no scale) — the estimator the
+    reference selects in Open3D (TransformationEstimationPointToPoint(False), utils/open3d_func.py:46), by SVD in fp64."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    ca, cb = a.mean(0), b.mean(0)
+    H = (a - ca).T @ (b - cb)
+    U, _, Vt = np.linalg.svd(H)
+    D = np.diag([1.0, 1.0, np.sign(np.linalg.det(Vt.T @ U.T))])
+    R = Vt.T @ D @ U.T
+    T = np.eye(4); T[:3, :3] = R; T[:3, 3] = cb - R @ ca
+    return T
+
+
+def count_inliers(T, a, b, dist):
+    d = apply_transform_2dim_numpy(np.asarray(a, np.float64), np.asarray(T, np.float64)) - b
+    return int((np.linalg.norm(d, axis=1) < dist).sum())

@@ -440,3 +440,77 @@ void ri_oracle_grouping_grad(const float *grad_y, const int *idx, int B, int C, 
             for (size_t e = 0; e < (size_t)M * U; ++e)
                 grad_x[((size_t)b * C + l) * N + idx[(size_t)b * M * U + e]] += grad_y[((size_t)b * C + l) * M * U + e];
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Barycentre grid subsampling.  cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.cpp:4-106
+ * (SampledData: grid_subsampling.h:9-84; PointXYZ float arithmetic: cpp_wrappers/cpp_utils/cloud/cloud.h:40-155).
+ * points [N,3], features [N,fdim] or NULL, labels [N,ldim] or NULL -> out_* for M cells, returns M.
+ * The reference emits cells in unordered_map iteration order (unspecified); here: ASCENDING cell index.
+ * Label ties: the reference returns the first maximum in the inner unordered_map's iteration order
+ * (unspecified); here: the smallest label.  keys_out (optional, [N]) receives each output cell's index.
+ * -----------------------------------------------------------------------------------------------*/
+typedef struct { uint64_t key; int idx; } ri_gs_pair;
+static int ri_gs_cmp(const void *a, const void *b)
+{
+    const ri_gs_pair *x = (const ri_gs_pair *)a, *y = (const ri_gs_pair *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx ? 1 : 0);          /* original point order inside a cell */
+}
+
+int ri_oracle_grid_subsample(const float *pts, const float *feats, const int *labels, int N, int fdim, int ldim,
+                             float dl, float *out_pts, float *out_feats, int *out_labels, uint64_t *keys_out)
+{
+    if (N <= 0) return 0;
+    float mn[3] = {pts[0], pts[1], pts[2]}, mx[3] = {pts[0], pts[1], pts[2]};
+    for (int i = 1; i < N; ++i)
+        for (int a = 0; a < 3; ++a) {
+            float v = pts[3 * (size_t)i + a];
+            if (v < mn[a]) mn[a] = v;
+            if (v > mx[a]) mx[a] = v;
+        }
+    const float inv = 1 / dl;                                          /* :27  (1/sampleDl) */
+    float org[3];
+    for (int a = 0; a < 3; ++a) org[a] = floorf(mn[a] * inv) * dl;     /* :27 */
+    const uint64_t nx = (uint64_t)floorf((mx[0] - org[0]) / dl) + 1;   /* :30 */
+    const uint64_t ny = (uint64_t)floorf((mx[1] - org[1]) / dl) + 1;   /* :31 */
+    ri_gs_pair *pr = (ri_gs_pair *)malloc((size_t)N * sizeof(ri_gs_pair));
+    for (int i = 0; i < N; ++i) {
+        const uint64_t ix = (uint64_t)floorf((pts[3 * (size_t)i + 0] - org[0]) / dl);     /* :53-56 */
+        const uint64_t iy = (uint64_t)floorf((pts[3 * (size_t)i + 1] - org[1]) / dl);
+        const uint64_t iz = (uint64_t)floorf((pts[3 * (size_t)i + 2] - org[2]) / dl);
+        pr[i].key = ix + nx * iy + nx * ny * iz;
+        pr[i].idx = i;
+    }
+    qsort(pr, (size_t)N, sizeof(ri_gs_pair), ri_gs_cmp);
+    int M = 0;
+    for (int s0 = 0; s0 < N;) {
+        int s1 = s0;
+        while (s1 < N && pr[s1].key == pr[s0].key) ++s1;
+        const int cnt = s1 - s0;
+        for (int a = 0; a < 3; ++a) {
+            float acc = 0.0f;
+            for (int s = s0; s < s1; ++s) acc = acc + pts[3 * (size_t)pr[s].idx + a];     /* point += p, original order */
+            out_pts[3 * (size_t)M + a] = acc * (float)(1.0 / cnt);                         /* :84 point * (1.0 / count) */
+        }
+        for (int f = 0; f < fdim; ++f) {
+            float acc = 0.0f;
+            for (int s = s0; s < s1; ++s) acc = acc + feats[(size_t)pr[s].idx * fdim + f];
+            out_feats[(size_t)M * fdim + f] = acc / (float)cnt;                            /* :88-92 */
+        }
+        for (int l = 0; l < ldim; ++l) {
+            int best = 0, best_n = 0;
+            for (int s = s0; s < s1; ++s) {
+                const int v = labels[(size_t)pr[s].idx * ldim + l];
+                int n = 0;
+                for (int t = s0; t < s1; ++t) n += labels[(size_t)pr[t].idx * ldim + l] == v;
+                if (n > best_n || (n == best_n && v < best)) { best = v; best_n = n; }
+            }
+            out_labels[(size_t)M * ldim + l] = best;                                       /* :96-100 */
+        }
+        if (keys_out) keys_out[M] = pr[s0].key;
+        ++M;
+        s0 = s1;
+    }
+    free(pr);
+    return M;
+}

@@ -10,6 +10,8 @@ Layout:
     modules/        the reference's PVCNN.modules hot-path classes (Voxelization, Spherical_Voxelization, knnModule, PVConv)
     frontend.py     the fused, graph-captured front-end engine (what bench.py measures)
     matcher.py      mutual-nearest-neighbour descriptor matching
+    registration.py matches -> RANSAC / Kabsch pose -> RRE / RTE / RMSE meter (the reference's registration meter)
+    subsampling.py  barycentre grid subsampling (the reference's utils/grid_subsampleing.py API)
     shard.py        one-process-per-GPU sharding helpers
     synth.py        seeded synthetic inputs
 """
@@ -18,6 +20,7 @@ from . import ops             # noqa: F401  registers torch.ops.ri.*
 from .backend import _backend  # noqa: F401
 from . import functional, modules  # noqa: F401
 from .frontend import FrontEnd, FrontEndLanes, FrontEndPipeline  # noqa: F401
-from . import shard, synth, matcher  # noqa: F401
+from . import shard, synth, matcher, subsampling, registration  # noqa: F401
+from .subsampling import grid_sub_sampling  # noqa: F401
 
 __version__ = '0.1.0'

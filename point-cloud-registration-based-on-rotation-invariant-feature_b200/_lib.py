@@ -43,6 +43,11 @@ SIGNATURES = {
     "ri_ball_query_f32": (_I, [_P, _P, _I, _I, _I, ctypes.c_float, _I, _P, _P]),
     "ri_grouping_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "ri_grouping_backward_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "ri_grid_subsample_workspace_bytes": (_Z, [_I]),
+    "ri_grid_subsample_f32": (_I, [_P, _P, _P, _I, _I, _I, ctypes.c_float, _P, _P, _P, _P, _P, _Z, _P]),
+    "ri_pose_from_matches_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, ctypes.c_float, ctypes.c_float, _I,
+                                     ctypes.c_ulonglong, _P, _P, _P, _P]),
+    "ri_registration_metrics_f32": (_I, [_P, _P, _P, _I, _I, _P, _P]),
     "ri_mutual_nn_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "ri_mutual_nn_tf32x3": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
 }

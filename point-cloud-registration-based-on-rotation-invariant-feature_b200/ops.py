@@ -498,3 +498,81 @@ def _(desc1, desc2, point_major):
     n2 = desc2.shape[1] if point_major else desc2.shape[2]
     i = lambda *s: desc1.new_empty(s, dtype=torch.int32)
     return i(P, n1), i(P, n2), desc1.new_empty((P, n1)), i(P, n1), i(P, n1), i(P)
+
+
+# ---------------------------------------------------------------------------------------------- grid subsampling (f2)
+@torch.library.custom_op("ri::grid_subsample", mutates_args=())
+def grid_subsample(points: torch.Tensor, features: torch.Tensor, labels: torch.Tensor, grid_size: float) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """points [N,3] f32, features [N,d] f32 (d may be 0), labels [N,l] i32 (l may be 0) -> (sub_points [N,3], sub_features
+    [N,d], sub_labels [N,l], count [1] i32): the first count[0] rows are the cells in ascending cell index
+    (csrc/gridsub.cu; reference grid_subsampling.cpp:4-106).  No host synchronisation."""
+    _req(points, "points", torch.float32); _req(features, "features", torch.float32); _req(labels, "labels", torch.int32)
+    dev = _same_device(points, features, labels)
+    N = points.shape[0]
+    fdim, ldim = features.shape[1], labels.shape[1]
+    with torch.cuda.device(dev):
+        op = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        of = torch.empty((N, fdim), dtype=torch.float32, device=dev)
+        ol = torch.empty((N, ldim), dtype=torch.int32, device=dev)
+        cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+        nws = _L.ri_grid_subsample_workspace_bytes(N)
+        ws = torch.empty(max(nws, 256), dtype=torch.uint8, device=dev)
+        _check(_L.ri_grid_subsample_f32(points.data_ptr(), features.data_ptr() if fdim else None,
+                                        labels.data_ptr() if ldim else None, N, fdim, ldim, float(grid_size),
+                                        op.data_ptr(), of.data_ptr() if fdim else None, ol.data_ptr() if ldim else None,
+                                        cnt.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "ri_grid_subsample")
+    return op, of, ol, cnt
+
+
+@grid_subsample.register_fake
+def _(points, features, labels, grid_size):
+    N = points.shape[0]
+    return (points.new_empty((N, 3)), features.new_empty((N, features.shape[1])),
+            labels.new_empty((N, labels.shape[1])), labels.new_empty((1,)))
+
+
+# ---------------------------------------------------------------------------------------------- pose + metrics (f3)
+@torch.library.custom_op("ri::pose_from_matches", mutates_args=())
+def pose_from_matches(src: torch.Tensor, tgt: torch.Tensor, idx1: torch.Tensor, idx2: torch.Tensor, count: torch.Tensor,
+                      hyps: int, inlier_dist: float, edge_similarity: float, refine_iters: int, seed: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """src [P,n1,3], tgt [P,n2,3] f32; idx1/idx2 [P,ld], count [P] i32 (mutual matches) -> (T [P,4,4] f32 src->tgt,
+    inliers [P] i32).  hyps == 0: least squares over all matches.  csrc/pose.cu."""
+    _req(src, "src", torch.float32); _req(tgt, "tgt", torch.float32)
+    _req(idx1, "idx1", torch.int32); _req(idx2, "idx2", torch.int32); _req(count, "count", torch.int32)
+    dev = _same_device(src, tgt, idx1, idx2, count)
+    P, n1, _ = src.shape
+    n2 = tgt.shape[1]
+    ld = idx1.shape[1]
+    with torch.cuda.device(dev):
+        T = torch.empty((P, 4, 4), dtype=torch.float32, device=dev)
+        inl = torch.empty((P,), dtype=torch.int32, device=dev)
+        best = torch.empty((max(P, 1),), dtype=torch.int64, device=dev)
+        _check(_L.ri_pose_from_matches_f32(src.data_ptr(), tgt.data_ptr(), idx1.data_ptr(), idx2.data_ptr(), count.data_ptr(),
+                                           P, n1, n2, ld, int(hyps), float(inlier_dist), float(edge_similarity),
+                                           int(refine_iters), int(seed) & 0xFFFFFFFFFFFFFFFF, T.data_ptr(), inl.data_ptr(),
+                                           best.data_ptr(), _stream()), "ri_pose_from_matches")
+    return T, inl
+
+
+@pose_from_matches.register_fake
+def _(src, tgt, idx1, idx2, count, hyps, inlier_dist, edge_similarity, refine_iters, seed):
+    P = src.shape[0]
+    return src.new_empty((P, 4, 4)), count.new_empty((P,))
+
+
+@torch.library.custom_op("ri::registration_metrics", mutates_args=())
+def registration_metrics(gt: torch.Tensor, est: torch.Tensor, pts: torch.Tensor) -> torch.Tensor:
+    """gt, est [P,4,4] f32, pts [P,n,3] f32 -> [P,3] f64 = (RRE degrees, RTE, RMSE), deepgmr_mn40.py:121-126,152-164."""
+    _req(gt, "gt", torch.float32); _req(est, "est", torch.float32); _req(pts, "pts", torch.float32)
+    dev = _same_device(gt, est, pts)
+    P, n, _ = pts.shape
+    with torch.cuda.device(dev):
+        out = torch.empty((P, 3), dtype=torch.float64, device=dev)
+        _check(_L.ri_registration_metrics_f32(gt.data_ptr(), est.data_ptr(), pts.data_ptr(), P, n, out.data_ptr(), _stream()),
+               "ri_registration_metrics")
+    return out
+
+
+@registration_metrics.register_fake
+def _(gt, est, pts):
+    return gt.new_empty((gt.shape[0], 3), dtype=torch.float64)

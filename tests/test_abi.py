@@ -58,6 +58,8 @@ def test_ctypes_table_matches_header(built_lib):
                 assert t is ctypes.c_void_p, (name, a)
             elif a.startswith("size_t"):
                 assert t is ctypes.c_size_t, (name, a)
+            elif a.startswith("unsigned long long"):
+                assert t is ctypes.c_ulonglong, (name, a)
             elif a.startswith("long long"):
                 assert t is ctypes.c_longlong, (name, a)
             elif a.startswith("float"):
