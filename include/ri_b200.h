@@ -239,6 +239,15 @@ int ri_pose_from_matches_f32(const float* src, const float* tgt, const int* idx1
 int ri_registration_metrics_f32(const float* gt, const float* est, const float* pts, int P, int n, double* out,
                                 void* stream);
 
+/* ---- 'change_coords' rotation-invariant preprocessing -------------------------------------------
+ * The Python double loop of PVCNN_classifier.forward, rot_invariant_preprocess == 'change_coords'
+ * (PVCNN/models/pvcnn_classify.py:153-184), as one kernel: per cloud a frame from the farthest point and the farthest
+ * point not (anti)parallel to it (|cos| < 0.9), Gram-Schmidt, and the coordinates expressed in that frame.
+ * coords [B,cstride,N] (cstride 3 or 6, first three planes used), mean [B,3] = torch's coords.mean(2), norm_mode as in
+ * ri_vox_prologue_f32  ->  out [B,3,N], bases [B,3,3] (rows x, y, z; may be NULL), ok [B] (0 where the reference asserts). */
+int ri_lrf_change_coords_f32(const float* coords, int cstride, const float* mean, int B, int N, int norm_mode,
+                             float* out, float* bases, int* ok, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -327,3 +327,45 @@ def kabsch(a, b):
 def count_inliers(T, a, b, dist):
     d = apply_transform_2dim_numpy(np.asarray(a, np.float64), np.asarray(T, np.float64)) - b
     return int((np.linalg.norm(d, axis=1) < dist).sum())
+
+
+# ---------------------------------------------------------------------------------------------- LRF change_coords (row f4)
+def change_coords(coords, mean=None):
+    """PVCNN/models/pvcnn_classify.py:153-184, float32 numpy, loop for loop.  coords [B,3,N] -> (new [B,3,N], ok [B]).
+    `mean` [B,3]: the per-cloud mean to use (pass torch's to see the same bits); default numpy's."""
+    f32 = np.float32
+    coords = _f(coords)
+    b, _, n = coords.shape
+    m = coords.mean(axis=2, dtype=f32) if mean is None else _f(mean)
+    norm_coords = coords - m[:, :, None]                                            # :154
+    nrm = lambda v: f32(np.sqrt(f32(f32(f32(v[0] * v[0]) + f32(v[1] * v[1])) + f32(v[2] * v[2]))))
+    radius = np.sqrt((norm_coords[:, 0] ** 2 + norm_coords[:, 1] ** 2) + norm_coords[:, 2] ** 2).astype(f32)
+    rank = np.argsort(-radius, axis=1, kind="stable")                               # :155 (ties: lowest index first)
+    out = np.zeros((b, 3, n), f32); ok = np.zeros(b, np.int32)
+    for i in range(b):
+        base_x = norm_coords[i, :, rank[i, 0]]                                      # :159
+        if not nrm(base_x) > 1e-5:                                                  # :160 assert
+            continue
+        base_x = base_x / nrm(base_x)
+        found = False
+        for j in range(1, n):                                                       # :162-169
+            base_y = norm_coords[i, :, rank[i, j]]
+            if nrm(base_y) < 1e-5:
+                continue
+            base_y = base_y / nrm(base_y)
+            lamda = f32(f32(f32(base_x[0] * base_y[0]) + f32(base_x[1] * base_y[1])) + f32(base_x[2] * base_y[2]))
+            if lamda < 0.9 and lamda > -0.9:
+                found = True
+                break
+        if not found:                                                               # :170 assert
+            continue
+        d = f32(f32(f32(base_x[0] * base_y[0]) + f32(base_x[1] * base_y[1])) + f32(base_x[2] * base_y[2]))
+        base_x = (base_x - base_y * d).astype(f32)                                  # :175
+        if nrm(base_x) < 1e-5:                                                      # :176 assert
+            continue
+        base_x = base_x / nrm(base_x)                                               # :177
+        base_z = np.cross(base_x, base_y).astype(f32)                               # :179
+        base_z = base_z / nrm(base_z)                                               # :180
+        out[i, 0] = base_x @ norm_coords[i]; out[i, 1] = base_y @ norm_coords[i]; out[i, 2] = base_z @ norm_coords[i]   # :181-184
+        ok[i] = 1
+    return out, ok

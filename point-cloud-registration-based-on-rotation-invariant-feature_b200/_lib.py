@@ -48,6 +48,7 @@ SIGNATURES = {
     "ri_pose_from_matches_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, ctypes.c_float, ctypes.c_float, _I,
                                      ctypes.c_ulonglong, _P, _P, _P, _P]),
     "ri_registration_metrics_f32": (_I, [_P, _P, _P, _I, _I, _P, _P]),
+    "ri_lrf_change_coords_f32": (_I, [_P, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
     "ri_mutual_nn_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "ri_mutual_nn_tf32x3": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
 }

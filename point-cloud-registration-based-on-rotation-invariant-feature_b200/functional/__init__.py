@@ -7,3 +7,4 @@ from .ppf import ppf, knn_ppf, knn_ppf_fused
 from .knn import k_nearest_neighbor, knn_indices
 from .edge import voxel_edge_features
 from .ball_query import ball_query, grouping
+from .lrf import change_coords, global_ppf

@@ -576,3 +576,28 @@ def registration_metrics(gt: torch.Tensor, est: torch.Tensor, pts: torch.Tensor)
 @registration_metrics.register_fake
 def _(gt, est, pts):
     return gt.new_empty((gt.shape[0], 3), dtype=torch.float64)
+
+
+# ---------------------------------------------------------------------------------------------- LRF change_coords (f4)
+@torch.library.custom_op("ri::lrf_change_coords", mutates_args=())
+def lrf_change_coords(coords: torch.Tensor, mean: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """coords [B,3,N] or [B,6,N] f32, mean [B,3] f32 (coords[:, :3].mean(2)) -> (new_coords [B,3,N], bases [B,3,3], ok [B] i32).
+    csrc/lrf.cu; reference PVCNN/models/pvcnn_classify.py:153-184."""
+    _req(coords, "coords", torch.float32); _req(mean, "mean", torch.float32)
+    dev = _same_device(coords, mean)
+    B, cs, N = coords.shape
+    if cs not in (3, 6):
+        raise RuntimeError("coords must be [B,3,N] or [B,6,N]")
+    with torch.cuda.device(dev):
+        out = torch.empty((B, 3, N), dtype=torch.float32, device=dev)
+        bases = torch.empty((B, 3, 3), dtype=torch.float32, device=dev)
+        ok = torch.empty((B,), dtype=torch.int32, device=dev)
+        _check(_L.ri_lrf_change_coords_f32(coords.data_ptr(), cs, mean.data_ptr(), B, N, 1, out.data_ptr(), bases.data_ptr(),
+                                           ok.data_ptr(), _stream()), "ri_lrf_change_coords")
+    return out, bases, ok
+
+
+@lrf_change_coords.register_fake
+def _(coords, mean):
+    B, _, N = coords.shape
+    return coords.new_empty((B, 3, N)), coords.new_empty((B, 3, 3)), coords.new_empty((B,), dtype=torch.int32)
