@@ -339,7 +339,8 @@ static int sd_launch(const SdPlan& pl, const float* coords, const float* feat, i
                      float* outs, int* inds, float* wgts, cudaStream_t st)
 {
     auto kern = devox_stream_kernel<P>;
-    const size_t smem = (size_t)pl.R * pl.slot_bytes;
+    size_t smem = (size_t)pl.R * pl.slot_bytes;
+    if (const char* ev = getenv("RI_DEVOX_PAD_KB")) { const int v = atoi(ev); if (v >= 0 && v <= 64) smem += (size_t)v << 10; }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     ri_prefer_step_carveout(kern);

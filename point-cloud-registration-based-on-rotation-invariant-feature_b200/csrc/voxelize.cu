@@ -776,7 +776,8 @@ int vox_fill_launch(int B, int C, int N, int s, int b0, int b1, const VoxPlan& p
     int ring = kRing, ctas_per_sm = kFillCtasPerSm;
     if (const char* ev = getenv("RI_FILL_RING")) { const int v = atoi(ev); if (v >= 3 && v <= 6) ring = v; }
     if (const char* ev = getenv("RI_FILL_CTAS")) { const int v = atoi(ev); if (v >= 1 && v <= 2) ctas_per_sm = v; }
-    const size_t smem2 = (size_t)ring * plan.tile_cells * sizeof(float);
+    size_t smem2 = (size_t)ring * plan.tile_cells * sizeof(float);
+    if (const char* ev = getenv("RI_FILL_PAD_KB")) { const int v = atoi(ev); if (v >= 0 && v <= 64) smem2 += (size_t)v << 10; }
     auto kern = ring == 3 ? vox_fill_kernel<3> : ring == 4 ? vox_fill_kernel<4> : ring == 5 ? vox_fill_kernel<5> : vox_fill_kernel<6>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     if (e != cudaSuccess) return (int)e;

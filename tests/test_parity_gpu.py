@@ -510,3 +510,44 @@ def test_pipeline_matches_single_engine(ri):
     for a, b in zip(want, got):
         for n in a:
             assert torch.equal(a[n], b[n]), n
+
+
+@pytest.mark.parametrize("shape", ["cube", "spherical"])
+def test_lanes_match_serial_engine(ri, shape):
+    """FrontEndLanes (three batches in flight on three launch streams) leaves in every engine exactly what a serial replay
+    of that engine leaves — concurrency changes no bit."""
+    B, N, C, k, r = 8, 1024, 11, 20, 32
+    engines, want = [], []
+    for q in range(3):
+        fe = ri.FrontEnd(B, N, C, k=k, r=r, voxel_shape=shape)
+        fe.load(clouds(B, N, 300 + q), np.random.default_rng(q).standard_normal((B, C, N)).astype(np.float32))
+        fe.forward(); torch.cuda.synchronize()
+        want.append({n: getattr(fe, n).clone() for n in ("ppf", "knn_idx", "grid", "cnt", "ind", "devox", "edge")})
+        for n in want[-1]:
+            getattr(fe, n).zero_()
+        engines.append(fe)
+    lanes = ri.FrontEndLanes(engines, lanes=3)
+    lanes.begin()
+    for i in range(9):
+        lanes.forward(i)
+    lanes.end()
+    torch.cuda.synchronize()
+    for fe, w in zip(engines, want):
+        for n, v in w.items():
+            assert torch.equal(getattr(fe, n), v), n
+
+
+@pytest.mark.parametrize("k,n,m", [(20, 1024, 1024), (8, 100, 777), (16, 1000, 3000), (32, 333, 64), (20, 5, 3)])
+def test_knn_ties_and_short_reference_sets_vs_oracle(ri, oracle, k, n, m):
+    """Every reference point duplicated (distance ties everywhere), queries sitting on references (d = 0), fewer references
+    than k, reference sets larger than one shared-memory tile: indices and distances equal the oracle's bit for bit."""
+    g = torch.Generator().manual_seed(k * 1000 + n)
+    x1 = torch.randn(3, 3, n, generator=g)
+    x2 = torch.randn(3, 3, m, generator=g)
+    x2[:, :, m // 2:] = x2[:, :, :m - m // 2]
+    x1[:, :, :min(n, m) // 4] = x2[:, :, :min(n, m) // 4]
+    x1, x2 = x1.cuda().contiguous(), x2.cuda().contiguous()
+    d1, d2, i1, i2 = torch.ops.ri.knn(x1, x2, k)
+    od1, od2, oi1, oi2 = oracle.knn(A(x1), A(x2), k)
+    assert np.array_equal(A(i1), oi1) and np.array_equal(A(i2), oi2)
+    assert np.array_equal(A(d1), od1) and np.array_equal(A(d2), od2)
