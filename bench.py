@@ -120,6 +120,7 @@ def traffic_from_profile(workload):
 
 # ===================================================================================================== ours
 def run_ours(args, rank, world, local):
+    import numpy as np
     import torch
     import ri_b200
     from ri_b200 import shard, synth
@@ -253,6 +254,22 @@ def run_ours(args, rank, world, local):
     m_steps = 20
     ms_match, w = timed(lambda i: mm(d1, d2), m_steps); windows.append(w)
     ms_match /= m_steps
+    # ... and what follows it on the GPU (row f3): RANSAC (1000 hypotheses per pair) + Horn refit + RRE/RTE/RMSE
+    src_p, tgt_p, Rg, tg = synth.make_pairs(MP, Mn, seed=77 + rank)
+    p1 = torch.from_numpy(np.ascontiguousarray(src_p[:, :3].transpose(0, 2, 1))).to(dev)
+    p2 = torch.from_numpy(np.ascontiguousarray(tgt_p[:, :3].transpose(0, 2, 1))).to(dev)
+    ident = torch.arange(Mn, dtype=torch.int32, device=dev)[None].repeat(MP, 1).contiguous()
+    cnt_p = torch.full((MP,), Mn, dtype=torch.int32, device=dev)
+    gt_T = torch.eye(4, device=dev)[None].repeat(MP, 1, 1); gt_T[:, :3, :3] = torch.from_numpy(Rg).to(dev); gt_T[:, :3, 3] = torch.from_numpy(tg).to(dev)
+
+    def pose_step(i):
+        T, _ = ri_b200.registration.estimate_poses(p1, p2, ident, ident, cnt_p, func='ransac', seed=i)
+        return ri_b200.registration.registration_metrics(gt_T, T, p1)
+    for _ in range(3):
+        pose_step(0)
+    ms_pose, w = timed(pose_step, m_steps); windows.append(w)
+    ms_pose /= m_steps
+    pose_rre = float(pose_step(0)[:, 0].max())
     del mm, d1, d2
 
     if rank != 0:
@@ -302,7 +319,9 @@ def run_ours(args, rank, world, local):
                     "useful_tflops": world * 2.0 * MP * Mn * Mn * MC / (ms_match * 1e-3) / 1e12,
                     "issued_tf32_tflops": world * 3 * 2.0 * MP * Mn * Mn * MC / (ms_match * 1e-3) / 1e12,
                     "note": "3xTF32 split precision: three tensor-core products per useful one; includes the re-tiling "
-                            "pre-pass and the fp32 distance re-evaluation"},
+                            "pre-pass and the fp32 distance re-evaluation",
+                    "pose": {"workload": "RANSAC 1000 hypotheses + Horn refit + RRE/RTE/RMSE, %d pairs x %d matches per GPU" % (MP, Mn),
+                             "ms_per_call": ms_pose, "pairs_per_s": world * MP / (ms_pose * 1e-3), "max_rre_deg": pose_rre}},
     }
     if world == 1:
         line["cpu_baseline"] = cpu_port_baseline(wl, batches[0])
