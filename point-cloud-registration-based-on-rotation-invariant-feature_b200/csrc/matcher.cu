@@ -33,8 +33,8 @@
 //                                        (ordered(d) << 32 | index): lowest index wins ties, as np.argmin does
 //                      warp 5            TMEM allocator; lane 0 issues tcgen05.mma.kind::tf32 (M128 N256 K8), 6 per
 //                                        stage; tcgen05.commit releases the stage / publishes the accumulator
-//   * match_finish   per pair: unpack c1/c2, mutual mask, ordered compaction (idx1, idx2, count), and the fp32 distance
-//                    of every row's match from the re-tiled descriptors (64 contiguous bytes per row and chunk).
+//   * match_dist     per row of every pair: unpack c1, mutual flag, and the fp32 distance of the row's match from the
+//                    re-tiled descriptors;  match_compact  per pair: c2 and the ordered compaction (idx1, idx2, count).
 #include "ri_common.cuh"
 
 namespace {
@@ -43,7 +43,14 @@ constexpr int kTileM = 128;          // rows of f1 per CTA (TMEM lanes)
 constexpr int kTileN = 256;          // rows of f2 per CTA (TMEM columns)
 constexpr int kChunkK = 16;          // channels per pipeline stage (2 UMMA K-steps of 8 tf32)
 constexpr int kStages = 4;
-constexpr int kGemmThreads = 192;
+// The 'hi' operand of the 3xTF32 split is a with its low 13 mantissa bits cleared.  The tensor core ignores those bits of a
+// tf32 operand (truncation — pinned by tests/test_matcher_gpu.py::test_tensor_core_truncates_tf32_operands, which fails if it
+// ever rounds), so the raw fp32 tile IS the hi plane and the converters only write the lo plane: a third less shared-memory
+// traffic per stage.  Set to true to write the cleared values back explicitly.
+constexpr bool kWriteHi = false;
+constexpr int kConvGroups = 4;                           // converter warp groups; group g owns the stages kc % kConvGroups == g
+constexpr int kConvThreads = 128 * kConvGroups;
+constexpr int kGemmThreads = kConvThreads + 64;           // + TMA producer warp + MMA issuer warp
 constexpr int kRowBytes = kChunkK * 4;                       // 64 B of one row in one chunk
 constexpr int kABytes = kTileM * kRowBytes;                  // 8 KB  (one plane)
 constexpr int kBBytes = kTileN * kRowBytes;                  // 16 KB (one plane)
@@ -53,7 +60,7 @@ constexpr unsigned kLBO = 128, kSBO = 512;                   // see the image la
 __host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 struct MatchWs {                     // byte offsets inside the workspace
-    size_t img1, img2, nrm1, nrm2, rowkey, colkey, total;
+    size_t img1, img2, nrm1, nrm2, rowkey, colkey, mutual, total;
     int n1p, n2p, Cp;
 };
 __host__ __device__ inline MatchWs match_ws_layout(int P, int C, int n1, int n2)
@@ -70,6 +77,7 @@ __host__ __device__ inline MatchWs match_ws_layout(int P, int C, int n1, int n2)
     o = (o + 15) / 16 * 16;
     w.rowkey = o; o += (size_t)P * w.n1p * sizeof(unsigned long long);
     w.colkey = o; o += (size_t)P * w.n2p * sizeof(unsigned long long);
+    w.mutual = o; o += (size_t)P * w.n1p * sizeof(int);
     w.total = o;
     return w;
 }
@@ -87,43 +95,63 @@ __device__ __forceinline__ unsigned ordered_u32(float f)
 constexpr int kPrepRows = 64;
 constexpr int kPrepThreads = kPrepRows * 4;
 constexpr int kPrepLd = kPrepRows + 2;                       // 4*q*ld mod 32 = {0,8,16,24}: conflict-free chunk reads
+constexpr int kPrepStages = 4;                               // chunks in flight per CTA (cp.async groups)
 
-__global__ void __launch_bounds__(kPrepThreads)
-match_prep_kernel(const float* __restrict__ desc, int C, int n, int npad, int Cp, int point_major,
-                  float* __restrict__ img, float* __restrict__ nrm, unsigned long long* __restrict__ key)
+struct PrepSide { const float* desc; float* img; float* nrm; unsigned long long* key; int n, npad; };
+
+__device__ __forceinline__ void cp_async4(float* sdst, const float* gsrc)
 {
-    __shared__ float s[2][kChunkK * kPrepLd];
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(ri_smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+
+// Both descriptor sets in one launch (blockIdx.z = side).  The staging of a chunk is asynchronous (cp.async, one commit
+// group per chunk, kPrepStages - 1 chunks in flight): with plain loads every iteration exposed a full memory latency
+// (the shared-memory store waits for its load), 32 of them per CTA — 76 us per side where the traffic needs 22.
+__global__ void __launch_bounds__(kPrepThreads)
+match_prep_kernel(PrepSide s0, PrepSide s1, int C, int Cp, int point_major)
+{
+    __shared__ float s[kPrepStages][kChunkK * kPrepLd];
+    const PrepSide S = blockIdx.z == 0 ? s0 : s1;
+    const int n = S.n, npad = S.npad;
     const int cloud = blockIdx.y;
     const int r0 = blockIdx.x * kPrepRows;
+    if (r0 >= npad) return;
     const int u = threadIdx.x;                               // 16-byte chunk id inside the (64 rows x 16 ch) block
     const int i_loc = ((u >> 5) << 3) | (u & 7);
     const int q = (u >> 3) & 3;
-    const float* D = desc + (size_t)cloud * C * n;
-    float* I = img + (size_t)cloud * npad * Cp;
+    const float* D = S.desc + (size_t)cloud * C * n;
+    float* I = S.img + (size_t)cloud * npad * Cp;
     const size_t plane = (size_t)npad * kChunkK;             // floats per chunk
     const int nk = Cp / kChunkK;
     double acc = 0.0;
 
     auto stage = [&](int kc, float* dst) {
-        if (!point_major) {                                  // [C, n]: lanes walk rows (contiguous)
-            for (int e = u; e < kChunkK * kPrepRows; e += kPrepThreads) {
-                const int c = e / kPrepRows, i = e % kPrepRows;
-                const int gc = kc * kChunkK + c, gi = r0 + i;
-                dst[c * kPrepLd + i] = (gc < C && gi < n) ? __ldg(D + (size_t)gc * n + gi) : 0.f;
-            }
-        } else {                                             // [n, C]: lanes walk channels (contiguous)
-            for (int e = u; e < kChunkK * kPrepRows; e += kPrepThreads) {
-                const int c = e & 15, i = e >> 4;
-                const int gc = kc * kChunkK + c, gi = r0 + i;
-                dst[c * kPrepLd + i] = (gc < C && gi < n) ? __ldg(D + (size_t)gi * C + gc) : 0.f;
+        if (kc < nk) {
+            if (!point_major) {                              // [C, n]: lanes walk rows (contiguous)
+                for (int e = u; e < kChunkK * kPrepRows; e += kPrepThreads) {
+                    const int c = e / kPrepRows, i = e % kPrepRows;
+                    const int gc = kc * kChunkK + c, gi = r0 + i;
+                    if (gc < C && gi < n) cp_async4(dst + c * kPrepLd + i, D + (size_t)gc * n + gi);
+                    else dst[c * kPrepLd + i] = 0.f;
+                }
+            } else {                                         // [n, C]: lanes walk channels (contiguous)
+                for (int e = u; e < kChunkK * kPrepRows; e += kPrepThreads) {
+                    const int c = e & 15, i = e >> 4;
+                    const int gc = kc * kChunkK + c, gi = r0 + i;
+                    if (gc < C && gi < n) cp_async4(dst + c * kPrepLd + i, D + (size_t)gi * C + gc);
+                    else dst[c * kPrepLd + i] = 0.f;
+                }
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");  // one group per chunk, empty past the end
     };
-    stage(0, s[0]);
+#pragma unroll
+    for (int p = 0; p < kPrepStages - 1; ++p) stage(p, s[p]);
     for (int kc = 0; kc < nk; ++kc) {
-        __syncthreads();                                     // chunk kc staged; the other buffer is free again
-        if (kc + 1 < nk) stage(kc + 1, s[(kc + 1) & 1]);
-        const float* src = s[kc & 1];
+        asm volatile("cp.async.wait_group %0;" :: "n"(kPrepStages - 2) : "memory");   // chunk kc has landed (this thread's part)
+        __syncthreads();                                     // ... everyone's part; the buffer of chunk kc - 1 is free again
+        stage(kc + kPrepStages - 1, s[(kc + kPrepStages - 1) % kPrepStages]);
+        const float* src = s[kc % kPrepStages];
         float4 v;
         v.x = src[(4 * q + 0) * kPrepLd + i_loc]; v.y = src[(4 * q + 1) * kPrepLd + i_loc];
         v.z = src[(4 * q + 2) * kPrepLd + i_loc]; v.w = src[(4 * q + 3) * kPrepLd + i_loc];
@@ -136,8 +164,8 @@ match_prep_kernel(const float* __restrict__ desc, int C, int n, int npad, int Cp
     acc += __shfl_xor_sync(0xffffffffu, acc, 8);
     acc += __shfl_xor_sync(0xffffffffu, acc, 16);
     if (q == 0) {
-        nrm[(size_t)cloud * npad + r0 + i_loc] = (float)acc;
-        key[(size_t)cloud * npad + r0 + i_loc] = ~0ull;
+        S.nrm[(size_t)cloud * npad + r0 + i_loc] = (float)acc;
+        S.key[(size_t)cloud * npad + r0 + i_loc] = ~0ull;
     }
 }
 
@@ -254,19 +282,20 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         ri_fence_proxy_async_smem();
     }
-    if (warp == 5) {                                         // TMEM: 256 fp32 columns x 128 lanes
+    constexpr int kProdWarp = kConvThreads / 32, kMmaWarp = kProdWarp + 1;
+    if (warp == kMmaWarp) {                                  // TMEM: 256 fp32 columns x 128 lanes
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"(ri_smem_u32(&S->tmem_base)), "r"((uint32_t)kTileN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp < 4)
-        for (int j = t; j < kTileN; j += 128) S->n2[j] = nrm2[(size_t)pair * n2p + c0 + j];
+    if (warp < kProdWarp)
+        for (int j = t; j < kTileN; j += kConvThreads) S->n2[j] = nrm2[(size_t)pair * n2p + c0 + j];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S->tmem_base;
 
-    if (warp == 4) {
+    if (warp == kProdWarp) {
         if (lane == 0) {                                     // ---- TMA producer: raw fp32 tiles, 24 KB per stage
             const uint8_t* A = reinterpret_cast<const uint8_t*>(img1) + (size_t)pair * n1p * Cp * 4;
             const uint8_t* B = reinterpret_cast<const uint8_t*>(img2) + (size_t)pair * n2p * Cp * 4;
@@ -282,7 +311,7 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
                 bulk_g2s(dst + kBHi, B + (size_t)kc * planeB + (size_t)c0 * kRowBytes, kBBytes, bar);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kMmaWarp) {
         if (lane == 0) {                                     // ---- MMA issuer
             for (int kc = 0; kc < nk; ++kc) {
                 const int s = kc % kStages;
@@ -304,10 +333,14 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
             tc_commit(ri_smem_u32(&S->accum));               // accumulator complete
         }
     } else {
-        // ---- converters: thread t splits A-tile row t and B-tile rows t, t + 128 (4 k-core slots each) of every stage
-        const uint32_t slot_a = (uint32_t)(t >> 3) * kSBO + (uint32_t)(t & 7) * 16;        // row t inside a plane
-        const uint32_t slot_b1 = (uint32_t)((t + 128) >> 3) * kSBO + (uint32_t)(t & 7) * 16;
-        for (int kc = 0; kc < nk; ++kc) {
+        // ---- converters: thread tg of a group splits A-tile row tg and B-tile rows tg, tg + 128 (4 k-core slots each) of
+        //      the group's stages.  One stage is a serial chain for its four warps (wait -> 12 LDS -> split -> 24 STS ->
+        //      proxy fence -> arrive, ~2.4k clk against 768 clk of MMA work): with a single group the tensor pipe waited
+        //      on it (31 % busy); kConvGroups groups convert that many stages at the same time.
+        const int grp = t >> 7, tg = t & 127, wq = warp & 3;
+        const uint32_t slot_a = (uint32_t)(tg >> 3) * kSBO + (uint32_t)(tg & 7) * 16;      // row tg inside a plane
+        const uint32_t slot_b1 = (uint32_t)((tg + 128) >> 3) * kSBO + (uint32_t)(tg & 7) * 16;
+        for (int kc = grp; kc < nk; kc += kConvGroups) {
             const int s = kc % kStages;
             const uint32_t ph = (kc / kStages) & 1;
             mbar_wait(ri_smem_u32(&S->raw[s]), ph);
@@ -323,13 +356,13 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
             for (int q = 0; q < 4; ++q) {
                 float4 h, l;
                 split4(v[3 * q + 0], h, l);
-                *reinterpret_cast<float4*>(st + kAHi + slot_a + q * kLBO) = h;
+                if (kWriteHi) *reinterpret_cast<float4*>(st + kAHi + slot_a + q * kLBO) = h;
                 *reinterpret_cast<float4*>(st + kALo + slot_a + q * kLBO) = l;
                 split4(v[3 * q + 1], h, l);
-                *reinterpret_cast<float4*>(st + kBHi + slot_a + q * kLBO) = h;
+                if (kWriteHi) *reinterpret_cast<float4*>(st + kBHi + slot_a + q * kLBO) = h;
                 *reinterpret_cast<float4*>(st + kBLo + slot_a + q * kLBO) = l;
                 split4(v[3 * q + 2], h, l);
-                *reinterpret_cast<float4*>(st + kBHi + slot_b1 + q * kLBO) = h;
+                if (kWriteHi) *reinterpret_cast<float4*>(st + kBHi + slot_b1 + q * kLBO) = h;
                 *reinterpret_cast<float4*>(st + kBLo + slot_b1 + q * kLBO) = l;
             }
             ri_fence_proxy_async_smem();                     // generic-proxy stores -> visible to the tensor core's reads
@@ -337,16 +370,18 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
             if (lane == 0)
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(ri_smem_u32(&S->full[s])) : "memory");
         }
-        // ---- epilogue: warp w reads TMEM lanes [32w, 32w + 32) = tile rows, i.e. thread t <-> row t
-        const int gi = m0 + t;
+        // ---- epilogue: warp w reads TMEM lanes [32 (w % 4), +32) = tile rows (thread tg <-> row tg); group g takes the
+        //      columns [g * kTileN / kConvGroups, ...)
+        const int gi = m0 + tg;
         const bool row_ok = gi < n1;
         const float na = nrm1[(size_t)pair * n1p + gi];
         mbar_wait(ri_smem_u32(&S->accum), 0);
         tc_fence_after();
         float best = 0.f; int best_j = -1;
-        for (int cc = 0; cc < kTileN; cc += 32) {
+        constexpr int kColsPerGroup = kTileN / kConvGroups;
+        for (int cc = grp * kColsPerGroup; cc < (grp + 1) * kColsPerGroup; cc += 32) {
             uint32_t v[32];
-            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc, v);
+            tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)cc, v);
             unsigned long long mine = ~0ull;
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
@@ -357,14 +392,14 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
                 const unsigned mn = __reduce_min_sync(0xffffffffu, key);
                 const unsigned who = __ballot_sync(0xffffffffu, key == mn);
                 if (lane == e)
-                    mine = ((unsigned long long)mn << 32) | (unsigned)(m0 + warp * 32 + (__ffs(who) - 1));
+                    mine = ((unsigned long long)mn << 32) | (unsigned)(m0 + wq * 32 + (__ffs(who) - 1));
             }
-            S->colkey[warp][cc + lane] = mine;
+            S->colkey[wq][cc + lane] = mine;
         }
         if (row_ok && best_j >= 0)
             atomicMin(rowkey + (size_t)pair * n1p + gi, ((unsigned long long)ordered_u32(best) << 32) | (unsigned)best_j);
-        asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps
-        for (int j = t; j < kTileN; j += 128) {
+        asm volatile("bar.sync 1, %0;" :: "n"(kConvThreads) : "memory");       // all epilogue warps
+        for (int j = t; j < kTileN; j += kConvThreads) {
             if (c0 + j >= n2) continue;
             unsigned long long k0 = S->colkey[0][j];
             const unsigned long long k1 = S->colkey[1][j], k2 = S->colkey[2][j], k3 = S->colkey[3][j];
@@ -374,61 +409,74 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)kTileN) : "memory");
     }
 }
 
 // ------------------------------------------------------------------------------------------------ match_finish
-// One CTA per pair.  corr12[i] = argmin_j, corr21[j] = argmin_i, (idx1, idx2)[0..count) = the mutual matches in ascending
-// i (-1 beyond), dist12[i] = |f1_i - f2_corr12[i]|^2 accumulated in fp32 from the re-tiled descriptors (per 16-channel
-// chunk a row is 4 x 16 B at a 128 B stride: whole sectors, where the channel-major source would cost 512 sectors a row).
+// Two kernels.  match_dist: one thread per row of every pair — corr12[i] = argmin_j, the mutual flag, and dist12[i] =
+// |f1_i - f2_corr12[i]|^2 accumulated in fp32 from the re-tiled descriptors (per 16-channel chunk a row is 4 x 16 B at a
+// 128 B stride).  This is the part with the memory traffic (the two descriptor rows of every match), so it gets the whole
+// machine: as one CTA per pair it ran on 32 of the 148 SMs (106 us per 32 pairs).  match_compact: one CTA per pair —
+// corr21[j] = argmin_i and the ordered compaction (idx1, idx2)[0..count) of the mutual matches in ascending i (-1 beyond).
+constexpr int kDistThreads = 128;
+__global__ void __launch_bounds__(kDistThreads)
+match_dist_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int n1, int n2, int n1p, int n2p, int Cp,
+                  const unsigned long long* __restrict__ rowkey, const unsigned long long* __restrict__ colkey,
+                  int* __restrict__ corr12, float* __restrict__ dist12, int* __restrict__ mutual)
+{
+    const int p = blockIdx.y;
+    const int i = blockIdx.x * kDistThreads + threadIdx.x;
+    if (i >= n1) return;
+    const unsigned long long* RK = rowkey + (size_t)p * n1p;
+    const unsigned long long* CK = colkey + (size_t)p * n2p;
+    int j = (int)(unsigned)(RK[i] & 0xffffffffu);
+    const bool sane = (unsigned)j < (unsigned)n2;                    // false only if every distance of the row was NaN
+    if (!sane) j = 0;
+    corr12[(size_t)p * n1 + i] = j;
+    mutual[(size_t)p * n1p + i] = (sane && (int)(unsigned)(CK[j] & 0xffffffffu) == i) ? 1 : 0;
+    const size_t plane1 = (size_t)n1p * kChunkK, plane2 = (size_t)n2p * kChunkK;
+    const float* a = img1 + (size_t)p * n1p * Cp + (size_t)(i >> 3) * 128 + (size_t)(i & 7) * 4;
+    const float* b = img2 + (size_t)p * n2p * Cp + (size_t)(j >> 3) * 128 + (size_t)(j & 7) * 4;
+    const int nk = Cp / kChunkK;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};                             // no cancellation between norms and dot product
+    for (int kc = 0; kc < nk; ++kc) {
+        float4 x[4], y[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            x[q] = __ldg(reinterpret_cast<const float4*>(a + (size_t)kc * plane1 + q * 32));
+            y[q] = __ldg(reinterpret_cast<const float4*>(b + (size_t)kc * plane2 + q * 32));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float df = __fsub_rn(x[q].x, y[q].x); acc[0] = __fmaf_rn(df, df, acc[0]);
+            df = __fsub_rn(x[q].y, y[q].y); acc[1] = __fmaf_rn(df, df, acc[1]);
+            df = __fsub_rn(x[q].z, y[q].z); acc[2] = __fmaf_rn(df, df, acc[2]);
+            df = __fsub_rn(x[q].w, y[q].w); acc[3] = __fmaf_rn(df, df, acc[3]);
+        }
+    }
+    dist12[(size_t)p * n1 + i] = __fadd_rn(__fadd_rn(acc[0], acc[1]), __fadd_rn(acc[2], acc[3]));
+}
+
 constexpr int kFinThreads = 512;
 __global__ void __launch_bounds__(kFinThreads)
-match_finish_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int n1, int n2, int n1p, int n2p, int Cp,
-                    const unsigned long long* __restrict__ rowkey, const unsigned long long* __restrict__ colkey,
-                    int* __restrict__ corr12, int* __restrict__ corr21, float* __restrict__ dist12,
-                    int* __restrict__ idx1, int* __restrict__ idx2, int* __restrict__ count)
+match_compact_kernel(int n1, int n2, int n1p, int n2p, const unsigned long long* __restrict__ colkey,
+                     const int* __restrict__ corr12, const int* __restrict__ mutual_flag, int* __restrict__ corr21,
+                     int* __restrict__ idx1, int* __restrict__ idx2, int* __restrict__ count)
 {
     __shared__ int swarp[kFinThreads / 32];
     __shared__ int sbase;
     const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const unsigned long long* RK = rowkey + (size_t)p * n1p;
     const unsigned long long* CK = colkey + (size_t)p * n2p;
     for (int j = tid; j < n2; j += kFinThreads) corr21[(size_t)p * n2 + j] = (int)(unsigned)(CK[j] & 0xffffffffu);
-    const float* I1 = img1 + (size_t)p * n1p * Cp;
-    const float* I2 = img2 + (size_t)p * n2p * Cp;
-    const size_t plane1 = (size_t)n1p * kChunkK, plane2 = (size_t)n2p * kChunkK;
-    const int nk = Cp / kChunkK;
     if (tid == 0) sbase = 0;
     __syncthreads();
     for (int i0 = 0; i0 < n1; i0 += kFinThreads) {
         const int i = i0 + tid;
         int j = -1, mutual = 0;
-        if (i < n1) {
-            j = (int)(unsigned)(RK[i] & 0xffffffffu);
-            const bool sane = (unsigned)j < (unsigned)n2;            // false only if every distance of the row was NaN
-            if (!sane) j = 0;
-            corr12[(size_t)p * n1 + i] = j;
-            mutual = (sane && (int)(unsigned)(CK[j] & 0xffffffffu) == i) ? 1 : 0;
-            const float* a = I1 + (size_t)(i >> 3) * 128 + (size_t)(i & 7) * 4;
-            const float* b = I2 + (size_t)(j >> 3) * 128 + (size_t)(j & 7) * 4;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};                   // no cancellation between norms and dot product
-            for (int kc = 0; kc < nk; ++kc) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 x = __ldg(reinterpret_cast<const float4*>(a + (size_t)kc * plane1 + q * 32));
-                    const float4 y = __ldg(reinterpret_cast<const float4*>(b + (size_t)kc * plane2 + q * 32));
-                    float df = __fsub_rn(x.x, y.x); acc[0] = __fmaf_rn(df, df, acc[0]);
-                    df = __fsub_rn(x.y, y.y); acc[1] = __fmaf_rn(df, df, acc[1]);
-                    df = __fsub_rn(x.z, y.z); acc[2] = __fmaf_rn(df, df, acc[2]);
-                    df = __fsub_rn(x.w, y.w); acc[3] = __fmaf_rn(df, df, acc[3]);
-                }
-            }
-            dist12[(size_t)p * n1 + i] = __fadd_rn(__fadd_rn(acc[0], acc[1]), __fadd_rn(acc[2], acc[3]));
-        }
-        // ordered compaction of the mutual matches
+        if (i < n1) { j = corr12[(size_t)p * n1 + i]; mutual = mutual_flag[(size_t)p * n1p + i]; }
         const unsigned bal = __ballot_sync(0xffffffffu, mutual);
         const int before = __popc(bal & ((1u << lane) - 1));
         if (lane == 0) swarp[wid] = __popc(bal);
@@ -476,9 +524,9 @@ extern "C" int ri_mutual_nn_tf32x3(const float* desc1, const float* desc2, int P
     unsigned long long* rowkey = reinterpret_cast<unsigned long long*>(ws + L.rowkey);
     unsigned long long* colkey = reinterpret_cast<unsigned long long*>(ws + L.colkey);
 
-    match_prep_kernel<<<dim3(L.n1p / kPrepRows, P), kPrepThreads, 0, st>>>(desc1, C, n1, L.n1p, L.Cp, point_major, img1, nrm1, rowkey);
-    RI_LAUNCH_CHECK();
-    match_prep_kernel<<<dim3(L.n2p / kPrepRows, P), kPrepThreads, 0, st>>>(desc2, C, n2, L.n2p, L.Cp, point_major, img2, nrm2, colkey);
+    const PrepSide side1 = {desc1, img1, nrm1, rowkey, n1, L.n1p}, side2 = {desc2, img2, nrm2, colkey, n2, L.n2p};
+    const int prep_x = (L.n1p > L.n2p ? L.n1p : L.n2p) / kPrepRows;
+    match_prep_kernel<<<dim3(prep_x, P, 2), kPrepThreads, 0, st>>>(side1, side2, C, L.Cp, point_major);
     RI_LAUNCH_CHECK();
 
     const size_t smem = (size_t)kStages * kStageBytes + sizeof(GemmSmem) + 1024;
@@ -488,8 +536,11 @@ extern "C" int ri_mutual_nn_tf32x3(const float* desc1, const float* desc2, int P
         img1, img2, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp, rowkey, colkey);
     RI_LAUNCH_CHECK();
 
-    match_finish_kernel<<<P, kFinThreads, 0, st>>>(img1, img2, n1, n2, L.n1p, L.n2p, L.Cp, rowkey, colkey,
-                                                   corr12, corr21, dist12, idx1, idx2, count);
+    int* mutual = reinterpret_cast<int*>(ws + L.mutual);
+    match_dist_kernel<<<dim3((n1 + kDistThreads - 1) / kDistThreads, P), kDistThreads, 0, st>>>(
+        img1, img2, n1, n2, L.n1p, L.n2p, L.Cp, rowkey, colkey, corr12, dist12, mutual);
+    RI_LAUNCH_CHECK();
+    match_compact_kernel<<<P, kFinThreads, 0, st>>>(n1, n2, L.n1p, L.n2p, colkey, corr12, mutual, corr21, idx1, idx2, count);
     RI_LAUNCH_CHECK();
     return RI_OK;
 }

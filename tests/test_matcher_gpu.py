@@ -138,3 +138,23 @@ def test_matcher_errors(ri):
         torch.ops.ri.mutual_nn(a, torch.randn(2, 9, 16, device="cuda"), False)
     with pytest.raises(RuntimeError):
         torch.ops.ri.mutual_nn(a, torch.randn(3, 8, 16, device="cuda"), False)
+
+
+def test_tensor_core_truncates_tf32_operands():
+    """The GEMM feeds the RAW fp32 descriptor as the 'hi' operand and only writes the 'lo' plane (a - trunc(a)): that is
+    exact only if the tensor core ignores the low 13 mantissa bits of a tf32 operand (truncation), not if it rounds.  Pin it:
+    every channel of f1 is alpha = 1 + 0.75 * 2^-10 (rounds UP to 1 + 2^-10, truncates to 1); f2[0] = 0, f2[1] = beta * ones
+    with beta = 2 + 2^-9 chosen so that the true distances are |a|^2 and |a|^2 + 0.5, while a rounding tensor core would see
+    the second one 2.0 smaller and pick it."""
+    import ri_b200
+    C, n1 = 512, 128
+    alpha = np.float32(1 + 0.75 * 2.0 ** -10)
+    beta = np.float32(2 + 2.0 ** -9)
+    f1 = np.full((1, n1, C), alpha, np.float32)
+    f2 = np.zeros((1, 2, C), np.float32); f2[0, 1] = beta
+    x, y = f1[0].astype(np.float64), f2[0].astype(np.float64)
+    d = (x * x).sum(1)[:, None] + (y * y).sum(1)[None] - 2 * x @ y.T
+    assert 0.4 < d[0, 1] - d[0, 0] < 0.6
+    r = ri_b200.matcher.mutual_nn(torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda(), point_major=True)
+    assert int(r["corr12"].abs().sum()) == 0, "the tensor core rounded a tf32 operand: set kWriteHi = true in csrc/matcher.cu"
+    assert abs(float(r["dist12"][0, 0]) - d[0, 0]) <= 1e-5 * d[0, 0]
