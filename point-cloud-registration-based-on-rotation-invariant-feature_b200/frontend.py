@@ -63,9 +63,10 @@ class FrontEnd:
         if join_before_devox is None:
             # The cube devoxelizer streams the grid through shared memory (devox.cu, streaming form) and belongs to the same
             # L1/shared-memory split as the k-NN and the grid writer, so it starts as soon as the grid is written
-            # (measured step 192 -> 179 us).  The spherical one is the gather form, which wants the max-L1 split and so
-            # runs after the k-NN has left the SMs.
-            join_before_devox = voxel_shape != 'cube' or N > 2048 or r % 2 != 0 or 4 * r ** 3 > 256 * N
+            # (measured step 192 -> 179 us).  The spherical one (gather form) only touches the ~40 cells per plane its index
+            # quirks can reach, so its L1 appetite does not matter either (165 -> 158 us without the join).  Only the cube
+            # gather form (r = 64, N > 2048, odd r) lives off a large L1 and waits for the k-NN to leave the SMs.
+            join_before_devox = voxel_shape == 'cube' and (N > 2048 or r % 2 != 0 or 4 * r ** 3 > 256 * N)
         self.knn_after_front, self.join_before_devox = bool(knn_after_front), bool(join_before_devox)
         nb = -(-B // self.grid_chunks)
         self._chunks = [(b0, min(B, b0 + nb)) for b0 in range(0, B, nb)]

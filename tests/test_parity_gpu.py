@@ -200,7 +200,7 @@ def test_cube_voxelize_golden(ri, golden_dir, r):
 
 
 @pytest.mark.parametrize("B,N,C,r", [(32, 1024, 67, 32), (5, 1000, 9, 16), (3, 4096, 4, 64), (2, 777, 3, 8),
-                                      (2, 6000, 3, 32), (2, 500, 3, 5)])
+                                      (2, 6000, 3, 32), (2, 500, 3, 5), (1, 50000, 4, 64)])
 def test_sph_voxelize_vs_reference(ri, ref_backend, oracle, B, N, C, r):
     """Live against the reference kernels at full and odd sizes.  (N=6000 and r=5 take the atomic fallback path.)"""
     pts = clouds(B, N, 11 + r)

@@ -10,7 +10,7 @@ shape = os.environ.get("SHAPE", "cube")
 NE = 6
 fes = []
 for q in range(NE):
-    fe = ri_b200.FrontEnd(B, N, C, k=k, r=r, voxel_shape=shape)
+    fe = ri_b200.FrontEnd(B, N, C, k=k, r=r, voxel_shape=shape, join_before_devox={"0": False, "1": True}.get(os.environ.get("JOIN", ""), None))
     fe.load(synth.make_clouds(B, N, seed=q), synth.make_features(B, C, N, seed=q)); fes.append(fe)
 torch.cuda.synchronize()
 for ne in (int(os.environ.get("NE", 3)),):
