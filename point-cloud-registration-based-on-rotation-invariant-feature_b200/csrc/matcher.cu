@@ -48,9 +48,7 @@ constexpr int kStages = 4;
 // ever rounds), so the raw fp32 tile IS the hi plane and the converters only write the lo plane: a third less shared-memory
 // traffic per stage.  Set to true to write the cleared values back explicitly.
 constexpr bool kWriteHi = false;
-constexpr int kConvGroups = 4;                           // converter warp groups; group g owns the stages kc % kConvGroups == g
-constexpr int kConvThreads = 128 * kConvGroups;
-constexpr int kGemmThreads = kConvThreads + 64;           // + TMA producer warp + MMA issuer warp
+constexpr int kConvGroups = 3;                           // converter warp groups; group g owns the stages kc % kConvGroups == g
 constexpr int kRowBytes = kChunkK * 4;                       // 64 B of one row in one chunk
 constexpr int kABytes = kTileM * kRowBytes;                  // 8 KB  (one plane)
 constexpr int kBBytes = kTileN * kRowBytes;                  // 16 KB (one plane)
@@ -240,11 +238,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 struct GemmSmem {                                            // after the stage ring
     unsigned long long colkey[4][kTileN];                    // per epilogue warp, per column
     float n2[kTileN];
-    unsigned long long raw[kStages], full[kStages], empty[kStages], accum;
+    unsigned long long raw[kStages], full[kStages], empty[kStages], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
 
-// hi / lo split of 16-byte k-core slots, in place: x -> (x & 0xffffe000) at the same address, x - hi in the lo plane.
+// hi / lo split of 16-byte k-core slots: x -> (x & 0xffffe000), x - hi in the lo plane.
 // All loads are issued before the first store (the compiler must assume the stores alias the later loads otherwise,
 // which serialises twelve load -> store round trips per stage).
 __device__ __forceinline__ void split4(float4 v, float4& h, float4& l)
@@ -255,41 +253,71 @@ __device__ __forceinline__ void split4(float4 v, float4& h, float4& l)
     h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = __fsub_rn(v.w, h.w);
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// PERSISTENT: one CTA per SM walks the tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the stage ring runs on across tile
+// boundaries and the accumulator is double-buffered in TMEM (2 x 256 columns), so the epilogue of a tile, the pipeline
+// fill of the next one and every per-CTA start-up cost (launch, barrier init, TMEM allocation) overlap the tensor work
+// instead of adding to it.  Measured with one CTA per tile: T(C) = 92 us + 0.26 us x C for 32 pairs — at C = 512 the 7 waves of
+// tiles spent 40 % of the kernel outside their main loops.
+//   warps 0-7            epilogue (TMEM lanes 32 (w % 4) .., columns 128 (w / 4) ..): wait acc_full[buf] -> tcgen05.ld ->
+//                        keys -> arrive acc_empty[buf]
+//   warps 8 .. 8+4G-1    G converter groups, group g owns the stages with (global stage count) % G == g
+//   then                 one TMA producer warp, one MMA issuer / TMEM allocator warp
+constexpr int kEpiWarps = 8;                               // two per TMEM lane quarter, 128 columns each
+constexpr int kConvWarp0 = kEpiWarps;
+constexpr int kPThreads = 32 * (kEpiWarps + 4 * kConvGroups + 2);
+
+__global__ void __launch_bounds__(kPThreads, 1)
 match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
                   const float* __restrict__ nrm1, const float* __restrict__ nrm2,
-                  int n1, int n2, int n1p, int n2p, int Cp,
-                  unsigned long long* __restrict__ rowkey, unsigned long long* __restrict__ colkey)
+                  int n1, int n2, int n1p, int n2p, int Cp, int tiles_m, int tiles_n, int total_tiles,
+                  unsigned long long* __restrict__ rowkey, unsigned long long* __restrict__ colkey,
+                  unsigned long long* __restrict__ dbg)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     GemmSmem* S = reinterpret_cast<GemmSmem*>(smem + (size_t)kStages * kStageBytes);
+    // debug timeline (tools/exp_match_timeline.py): CTA 0 stamps %globaltimer at a few events of its first 8 tiles
+    auto stamp = [&](int it, int ev) {
+        if (dbg != nullptr && blockIdx.x == 0 && it < 8) {
+            unsigned long long tt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+            dbg[it * 8 + ev] = tt;
+        }
+    };
     const uint32_t ring = ri_smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
-    const int pair = blockIdx.z, m0 = blockIdx.y * kTileM, c0 = blockIdx.x * kTileN;
     const int nk = Cp / kChunkK;
     // stage layout: [A hi 8 KB][A lo 8 KB][B hi 16 KB][B lo 16 KB]; the raw fp32 tiles land in the hi regions
     constexpr int kAHi = 0, kALo = kABytes, kBHi = 2 * kABytes, kBLo = 2 * kABytes + kBBytes;
+    constexpr int kProdWarp = kConvWarp0 + 4 * kConvGroups, kMmaWarp = kProdWarp + 1;
+    const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    auto decode = [&](int it, int& pair, int& m0, int& c0) {
+        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const int per = tiles_m * tiles_n;
+        pair = tile / per;
+        const int rem = tile - pair * per;
+        m0 = (rem / tiles_n) * kTileM;
+        c0 = (rem - (rem / tiles_n) * tiles_n) * kTileN;
+    };
 
     if (t == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(ri_smem_u32(&S->raw[s]), 1);           // TMA producer's expect_tx arrival + the bytes
-            mbar_init(ri_smem_u32(&S->full[s]), 4);          // one arrival per converter warp and stage (128 per-thread
-                                                             // arrivals serialise on the barrier word: 2.7k clk per stage)
+            mbar_init(ri_smem_u32(&S->full[s]), 4);          // one arrival per converter warp of the owning group
             mbar_init(ri_smem_u32(&S->empty[s]), 1);         // tcgen05.commit
         }
-        mbar_init(ri_smem_u32(&S->accum), 1);
+        for (int q = 0; q < 2; ++q) {
+            mbar_init(ri_smem_u32(&S->acc_full[q]), 1);      // tcgen05.commit after a tile's last MMA
+            mbar_init(ri_smem_u32(&S->acc_empty[q]), kEpiWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         ri_fence_proxy_async_smem();
     }
-    constexpr int kProdWarp = kConvThreads / 32, kMmaWarp = kProdWarp + 1;
-    if (warp == kMmaWarp) {                                  // TMEM: 256 fp32 columns x 128 lanes
+    if (warp == kMmaWarp) {                                  // TMEM: 2 x 256 fp32 columns x 128 lanes
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(ri_smem_u32(&S->tmem_base)), "r"((uint32_t)kTileN) : "memory");
+                     :: "r"(ri_smem_u32(&S->tmem_base)), "r"((uint32_t)(2 * kTileN)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp < kProdWarp)
-        for (int j = t; j < kTileN; j += kConvThreads) S->n2[j] = nrm2[(size_t)pair * n2p + c0 + j];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -297,52 +325,69 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
 
     if (warp == kProdWarp) {
         if (lane == 0) {                                     // ---- TMA producer: raw fp32 tiles, 24 KB per stage
-            const uint8_t* A = reinterpret_cast<const uint8_t*>(img1) + (size_t)pair * n1p * Cp * 4;
-            const uint8_t* B = reinterpret_cast<const uint8_t*>(img2) + (size_t)pair * n2p * Cp * 4;
             const size_t planeA = (size_t)n1p * kRowBytes, planeB = (size_t)n2p * kRowBytes;
-            for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % kStages;
-                const uint32_t ph = (kc / kStages) & 1;
-                mbar_wait(ri_smem_u32(&S->empty[s]), ph ^ 1);
-                const uint32_t bar = ri_smem_u32(&S->raw[s]);
-                mbar_expect_tx(bar, kABytes + kBBytes);
-                const uint32_t dst = ring + s * kStageBytes;
-                bulk_g2s(dst + kAHi, A + (size_t)kc * planeA + (size_t)m0 * kRowBytes, kABytes, bar);
-                bulk_g2s(dst + kBHi, B + (size_t)kc * planeB + (size_t)c0 * kRowBytes, kBBytes, bar);
+            int g = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                int pair, m0, c0;
+                decode(it, pair, m0, c0);
+                const uint8_t* A = reinterpret_cast<const uint8_t*>(img1) + (size_t)pair * n1p * Cp * 4;
+                const uint8_t* B = reinterpret_cast<const uint8_t*>(img2) + (size_t)pair * n2p * Cp * 4;
+                for (int kc = 0; kc < nk; ++kc, ++g) {
+                    const int s = g % kStages;
+                    const uint32_t ph = (g / kStages) & 1;
+                    mbar_wait(ri_smem_u32(&S->empty[s]), ph ^ 1);
+                    const uint32_t bar = ri_smem_u32(&S->raw[s]);
+                    mbar_expect_tx(bar, kABytes + kBBytes);
+                    const uint32_t dst = ring + s * kStageBytes;
+                    bulk_g2s(dst + kAHi, A + (size_t)kc * planeA + (size_t)m0 * kRowBytes, kABytes, bar);
+                    bulk_g2s(dst + kBHi, B + (size_t)kc * planeB + (size_t)c0 * kRowBytes, kBBytes, bar);
+                }
             }
         }
     } else if (warp == kMmaWarp) {
         if (lane == 0) {                                     // ---- MMA issuer
-            for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % kStages;
-                const uint32_t ph = (kc / kStages) & 1;
-                mbar_wait(ri_smem_u32(&S->full[s]), ph);
+            int g = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int buf = it & 1;
+                stamp(it, 0);
+                mbar_wait(ri_smem_u32(&S->acc_empty[buf]), ((it >> 1) & 1) ^ 1);     // the epilogue has drained this buffer
                 tc_fence_after();
-                const uint32_t base = ring + s * kStageBytes;
+                stamp(it, 1);
+                const uint32_t acc = tmem + (uint32_t)(buf * kTileN);
+                for (int kc = 0; kc < nk; ++kc, ++g) {
+                    const int s = g % kStages;
+                    const uint32_t ph = (g / kStages) & 1;
+                    mbar_wait(ri_smem_u32(&S->full[s]), ph);
+                    tc_fence_after();
+                    const uint32_t base = ring + s * kStageBytes;
 #pragma unroll
-                for (int ks = 0; ks < kChunkK / 8; ++ks) {
-                    const uint32_t koff = ks * 2 * kLBO;     // one K-step = two 16-byte k-cores
-                    const uint64_t a_hi = smem_desc(base + kAHi + koff), a_lo = smem_desc(base + kALo + koff);
-                    const uint64_t b_hi = smem_desc(base + kBHi + koff), b_lo = smem_desc(base + kBLo + koff);
-                    tc_mma_tf32(tmem, a_lo, b_hi, kIdesc, (kc | ks) != 0);      // small terms first
-                    tc_mma_tf32(tmem, a_hi, b_lo, kIdesc, 1);
-                    tc_mma_tf32(tmem, a_hi, b_hi, kIdesc, 1);
+                    for (int ks = 0; ks < kChunkK / 8; ++ks) {
+                        const uint32_t koff = ks * 2 * kLBO;     // one K-step = two 16-byte k-cores
+                        const uint64_t a_hi = smem_desc(base + kAHi + koff), a_lo = smem_desc(base + kALo + koff);
+                        const uint64_t b_hi = smem_desc(base + kBHi + koff), b_lo = smem_desc(base + kBLo + koff);
+                        tc_mma_tf32(acc, a_lo, b_hi, kIdesc, (kc | ks) != 0);      // small terms first
+                        tc_mma_tf32(acc, a_hi, b_lo, kIdesc, 1);
+                        tc_mma_tf32(acc, a_hi, b_hi, kIdesc, 1);
+                    }
+                    tc_commit(ri_smem_u32(&S->empty[s]));        // stage reusable once these MMAs have read it
                 }
-                tc_commit(ri_smem_u32(&S->empty[s]));        // stage reusable once these MMAs have read it
+                tc_commit(ri_smem_u32(&S->acc_full[buf]));       // this tile's accumulator is complete
+                stamp(it, 2);
             }
-            tc_commit(ri_smem_u32(&S->accum));               // accumulator complete
         }
-    } else {
+    } else if (warp >= kConvWarp0) {
         // ---- converters: thread tg of a group splits A-tile row tg and B-tile rows tg, tg + 128 (4 k-core slots each) of
-        //      the group's stages.  One stage is a serial chain for its four warps (wait -> 12 LDS -> split -> 24 STS ->
-        //      proxy fence -> arrive, ~2.4k clk against 768 clk of MMA work): with a single group the tensor pipe waited
+        //      the group's stages.  One stage is a serial chain for its four warps (wait -> 12 LDS -> split -> 12 STS ->
+        //      proxy fence -> arrive, ~2.4k clk against 888 clk of MMA work): with a single group the tensor pipe waited
         //      on it (31 % busy); kConvGroups groups convert that many stages at the same time.
-        const int grp = t >> 7, tg = t & 127, wq = warp & 3;
+        const int ct = t - kConvWarp0 * 32;
+        const int grp = ct >> 7, tg = ct & 127;
         const uint32_t slot_a = (uint32_t)(tg >> 3) * kSBO + (uint32_t)(tg & 7) * 16;      // row tg inside a plane
         const uint32_t slot_b1 = (uint32_t)((tg + 128) >> 3) * kSBO + (uint32_t)(tg & 7) * 16;
-        for (int kc = grp; kc < nk; kc += kConvGroups) {
-            const int s = kc % kStages;
-            const uint32_t ph = (kc / kStages) & 1;
+        const int total = my_tiles * nk;
+        for (int g = grp; g < total; g += kConvGroups) {
+            const int s = g % kStages;
+            const uint32_t ph = (g / kStages) & 1;
             mbar_wait(ri_smem_u32(&S->raw[s]), ph);
             uint8_t* st = smem + (size_t)s * kStageBytes;
             float4 v[12];
@@ -370,48 +415,65 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
             if (lane == 0)
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(ri_smem_u32(&S->full[s])) : "memory");
         }
-        // ---- epilogue: warp w reads TMEM lanes [32 (w % 4), +32) = tile rows (thread tg <-> row tg); group g takes the
-        //      columns [g * kTileN / kConvGroups, ...)
-        const int gi = m0 + tg;
-        const bool row_ok = gi < n1;
-        const float na = nrm1[(size_t)pair * n1p + gi];
-        mbar_wait(ri_smem_u32(&S->accum), 0);
-        tc_fence_after();
-        float best = 0.f; int best_j = -1;
-        constexpr int kColsPerGroup = kTileN / kConvGroups;
-        for (int cc = grp * kColsPerGroup; cc < (grp + 1) * kColsPerGroup; cc += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)cc, v);
-            unsigned long long mine = ~0ull;
+    } else {
+        // ---- epilogue warps: warp w reads TMEM lanes [32 (w % 4), +32) = tile rows, columns [128 (w / 4), +128)
+        const int wq = warp & 3, half = warp >> 2, tr = t & 127;
+        constexpr int kColsPerHalf = kTileN / (kEpiWarps / 4);
+        for (int it = 0; it < my_tiles; ++it) {
+            int pair, m0, c0;
+            decode(it, pair, m0, c0);
+            const int buf = it & 1;
+            for (int j = t; j < kTileN; j += 32 * kEpiWarps) S->n2[j] = nrm2[(size_t)pair * n2p + c0 + j];
+            const int gi = m0 + tr;
+            const bool row_ok = gi < n1;
+            const float na = nrm1[(size_t)pair * n1p + gi];
+            asm volatile("bar.sync 1, %0;" :: "n"(32 * kEpiWarps) : "memory");        // n2 staged; previous tile's colkey consumed
+            if (t == 0) stamp(it, 3);
+            mbar_wait(ri_smem_u32(&S->acc_full[buf]), (it >> 1) & 1);
+            tc_fence_after();
+            if (t == 0) stamp(it, 4);
+            float best = 0.f; int best_j = -1;
+            for (int cc = half * kColsPerHalf; cc < (half + 1) * kColsPerHalf; cc += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * kTileN + cc), v);
+                unsigned long long mine = ~0ull;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-                const int j = c0 + cc + e;
-                const float d = __fmaf_rn(-2.0f, __uint_as_float(v[e]), __fadd_rn(na, S->n2[cc + e]));
-                if (j < n2 && (best_j < 0 || d < best)) { best = d; best_j = j; }
-                const unsigned key = row_ok ? ordered_u32(d) : 0xffffffffu;
-                const unsigned mn = __reduce_min_sync(0xffffffffu, key);
-                const unsigned who = __ballot_sync(0xffffffffu, key == mn);
-                if (lane == e)
-                    mine = ((unsigned long long)mn << 32) | (unsigned)(m0 + wq * 32 + (__ffs(who) - 1));
+                for (int e = 0; e < 32; ++e) {
+                    const int j = c0 + cc + e;
+                    const float d = __fmaf_rn(-2.0f, __uint_as_float(v[e]), __fadd_rn(na, S->n2[cc + e]));
+                    if (j < n2 && (best_j < 0 || d < best)) { best = d; best_j = j; }
+                    const unsigned key = row_ok ? ordered_u32(d) : 0xffffffffu;
+                    const unsigned mn = __reduce_min_sync(0xffffffffu, key);
+                    const unsigned who = __ballot_sync(0xffffffffu, key == mn);
+                    if (lane == e)
+                        mine = ((unsigned long long)mn << 32) | (unsigned)(m0 + wq * 32 + (__ffs(who) - 1));
+                }
+                S->colkey[wq][cc + lane] = mine;
             }
-            S->colkey[wq][cc + lane] = mine;
-        }
-        if (row_ok && best_j >= 0)
-            atomicMin(rowkey + (size_t)pair * n1p + gi, ((unsigned long long)ordered_u32(best) << 32) | (unsigned)best_j);
-        asm volatile("bar.sync 1, %0;" :: "n"(kConvThreads) : "memory");       // all epilogue warps
-        for (int j = t; j < kTileN; j += kConvThreads) {
-            if (c0 + j >= n2) continue;
-            unsigned long long k0 = S->colkey[0][j];
-            const unsigned long long k1 = S->colkey[1][j], k2 = S->colkey[2][j], k3 = S->colkey[3][j];
-            k0 = k1 < k0 ? k1 : k0; k0 = k2 < k0 ? k2 : k0; k0 = k3 < k0 ? k3 : k0;
-            if ((unsigned)(k0 >> 32) != 0xffffffffu) atomicMin(colkey + (size_t)pair * n2p + c0 + j, k0);
+            // the accumulator buffer has been read: hand it back to the MMA issuer before the (slow) global atomics
+            tc_fence_before();
+            __syncwarp();
+            if (t == 0) stamp(it, 5);
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(ri_smem_u32(&S->acc_empty[buf])) : "memory");
+            if (row_ok && best_j >= 0)
+                atomicMin(rowkey + (size_t)pair * n1p + gi, ((unsigned long long)ordered_u32(best) << 32) | (unsigned)best_j);
+            asm volatile("bar.sync 1, %0;" :: "n"(32 * kEpiWarps) : "memory");        // all column keys are in smem
+            for (int j = t; j < kTileN; j += 32 * kEpiWarps) {
+                if (c0 + j >= n2) continue;
+                unsigned long long k0 = S->colkey[0][j];
+                const unsigned long long k1 = S->colkey[1][j], k2 = S->colkey[2][j], k3 = S->colkey[3][j];
+                k0 = k1 < k0 ? k1 : k0; k0 = k2 < k0 ? k2 : k0; k0 = k3 < k0 ? k3 : k0;
+                if ((unsigned)(k0 >> 32) != 0xffffffffu) atomicMin(colkey + (size_t)pair * n2p + c0 + j, k0);
+            }
+            if (t == 0) stamp(it, 6);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == kMmaWarp) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)kTileN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)(2 * kTileN)) : "memory");
     }
 }
 
@@ -529,13 +591,20 @@ extern "C" int ri_mutual_nn_tf32x3(const float* desc1, const float* desc2, int P
     match_prep_kernel<<<dim3(prep_x, P, 2), kPrepThreads, 0, st>>>(side1, side2, C, L.Cp, point_major);
     RI_LAUNCH_CHECK();
 
-    const size_t smem = (size_t)kStages * kStageBytes + sizeof(GemmSmem) + 1024;
-    cudaError_t e = cudaFuncSetAttribute(match_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    match_gemm_kernel<<<dim3(L.n2p / kTileN, (n1 + kTileM - 1) / kTileM, P), kGemmThreads, smem, st>>>(
-        img1, img2, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp, rowkey, colkey);
-    RI_LAUNCH_CHECK();
-
+    {
+        const size_t smem = (size_t)kStages * kStageBytes + sizeof(GemmSmem) + 1024;
+        cudaError_t e = cudaFuncSetAttribute(match_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        const int tiles_m = (n1 + kTileM - 1) / kTileM, tiles_n = L.n2p / kTileN;
+        const long long total = (long long)P * tiles_m * tiles_n;
+        if (total > 0x7fffffffLL) return RI_ERR_UNSUPPORTED;
+        const int grid = total < ri_num_sms() ? (int)total : ri_num_sms();
+        match_gemm_kernel<<<grid, kPThreads, smem, st>>>(img1, img2, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp, tiles_m, tiles_n,
+                                                         (int)total, rowkey, colkey,
+                                                         reinterpret_cast<unsigned long long*>(getenv("RI_MATCH_DBG") ? ws + L.mutual : nullptr));
+        RI_LAUNCH_CHECK();
+        if (getenv("RI_MATCH_DBG")) return RI_OK;            // debug: keep the stamps (match_dist would overwrite them)
+    }
     int* mutual = reinterpret_cast<int*>(ws + L.mutual);
     match_dist_kernel<<<dim3((n1 + kDistThreads - 1) / kDistThreads, P), kDistThreads, 0, st>>>(
         img1, img2, n1, n2, L.n1p, L.n2p, L.Cp, rowkey, colkey, corr12, dist12, mutual);
