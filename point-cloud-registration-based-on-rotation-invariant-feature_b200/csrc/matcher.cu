@@ -48,7 +48,11 @@ constexpr int kStages = 4;
 // ever rounds), so the raw fp32 tile IS the hi plane and the converters only write the lo plane: a third less shared-memory
 // traffic per stage.  Set to true to write the cleared values back explicitly.
 constexpr bool kWriteHi = false;
-constexpr int kConvGroups = 3;                           // converter warp groups; group g owns the stages kc % kConvGroups == g
+constexpr int kConvGroups = 4;                           // converter warp groups; group g owns the stages kc % kConvGroups == g.
+// MUST divide kStages (static_assert below): a stage's barriers carry one phase bit, so every use of a stage has to be waited
+// for by the SAME warps in order.  With 3 groups over 4 stages a group met stage 0 only every third round, its early
+// try_wait(parity) was satisfied by another group's round of the same parity, it converted a tile that had not landed and
+// arrived on a barrier of the wrong round: about one call in a hundred deadlocked.
 constexpr int kRowBytes = kChunkK * 4;                       // 64 B of one row in one chunk
 constexpr int kABytes = kTileM * kRowBytes;                  // 8 KB  (one plane)
 constexpr int kBBytes = kTileN * kRowBytes;                  // 16 KB (one plane)
@@ -265,6 +269,7 @@ __device__ __forceinline__ void split4(float4 v, float4& h, float4& l)
 constexpr int kEpiWarps = 8;                               // two per TMEM lane quarter, 128 columns each
 constexpr int kConvWarp0 = kEpiWarps;
 constexpr int kPThreads = 32 * (kEpiWarps + 4 * kConvGroups + 2);
+static_assert(kStages % kConvGroups == 0, "each stage must belong to one converter group (one phase bit per barrier)");
 
 __global__ void __launch_bounds__(kPThreads, 1)
 match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2,

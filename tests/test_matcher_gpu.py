@@ -158,3 +158,25 @@ def test_tensor_core_truncates_tf32_operands():
     r = ri_b200.matcher.mutual_nn(torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda(), point_major=True)
     assert int(r["corr12"].abs().sum()) == 0, "the tensor core rounded a tf32 operand: set kWriteHi = true in csrc/matcher.cu"
     assert abs(float(r["dist12"][0, 0]) - d[0, 0]) <= 1e-5 * d[0, 0]
+
+
+def test_persistent_gemm_stress_two_streams():
+    """The persistent GEMM (stage ring across tiles, double-buffered TMEM accumulator, 22 warps in four roles) run 400 times,
+    alternating between two streams so that calls overlap on the device (TMEM allocation contention included), for three
+    shapes: every call must reproduce the first call's bits."""
+    import ri_b200
+    for (P, C, n1, n2) in ((32, 512, 1024, 1024), (5, 100, 300, 700), (64, 64, 128, 256)):
+        g = torch.Generator(device="cuda"); g.manual_seed(P)
+        d1 = torch.randn((P, C, n1), device="cuda", generator=g); d2 = torch.randn((P, C, n2), device="cuda", generator=g)
+        mms = [ri_b200.matcher.MutualMatcher(P, C, n1, n2) for _ in range(2)]
+        streams = [torch.cuda.Stream() for _ in range(2)]
+        mms[0](d1, d2); torch.cuda.synchronize()
+        want = (mms[0].corr12.clone(), mms[0].corr21.clone(), mms[0].dist12.clone(), mms[0].count.clone())
+        for it in range(400):
+            q = it & 1
+            with torch.cuda.stream(streams[q]):
+                mms[q](d1, d2)
+        torch.cuda.synchronize()
+        for mm in mms:
+            assert torch.equal(mm.corr12, want[0]) and torch.equal(mm.corr21, want[1])
+            assert torch.equal(mm.dist12, want[2]) and torch.equal(mm.count, want[3])
