@@ -186,6 +186,13 @@ int ri_voxel_edge_gather_f32(const float* avg, const float* feat, const int* ind
 int ri_ball_query_f32(const float* centers, const float* points, int B, int N, int M, float radius, int U,
                       int* neighbors, void* stream);
 
+/* The 'ppf' local features of the shipped models from the neighbour indices, without materialising the grouped tensors:
+ * PVCNN/models/pvcnn_classify.py:252-270 + PVCNN/modules/ball_query.py:16-35 (d = c - (p_nbr - c), |d|, three clamped acos
+ * of torch-ordered dot products, fp32).  points_* [B,3,N], centers_* [B,3,M], neighbors [B,M,U] -> out [B,4,U,M]. */
+int ri_local_ppf_f32(const float* points_coords, const float* points_normals, const float* centers_coords,
+                     const float* centers_normals, const int* neighbors, int B, int N, int M, int U,
+                     float* out, void* stream);
+
 /* grouping_forward / grouping_backward (grouping/grouping.cu:18-44, 58-84): out [B,C,M,U] = feat[b, c, idx[b, m, u]];
  * grad_x [B,C,N] += grad_y scattered through idx (float atomics, as the reference; grad_x is zeroed first). */
 int ri_grouping_f32(const float* feat, const int* idx, int B, int C, int N, int M, int U, float* out, void* stream);

@@ -369,3 +369,32 @@ def change_coords(coords, mean=None):
         out[i, 0] = base_x @ norm_coords[i]; out[i, 1] = base_y @ norm_coords[i]; out[i, 2] = base_z @ norm_coords[i]   # :181-184
         ok[i] = 1
     return out, ok
+
+
+# ---------------------------------------------------------------------------------------------- local PPF (row f1, fused)
+def local_ppf(points_coords, points_normals, neighbors, centers_coords=None, centers_normals=None):
+    """PVCNN/models/pvcnn_classify.py:252-270 on top of PVCNN/modules/ball_query.py:16-35, float32 numpy, operation for
+    operation: rel = p_nbr - c; d = c - rel; dn = sqrt((d0^2 + d1^2) + d2^2); du = d / dn; three clamped acos of dot products
+    summed as (p0 + p1) + p2.  points_* [B,3,N], neighbors [B,M,U] -> [B,4,U,M]."""
+    f32 = np.float32
+    pc, pn = _f(points_coords), _f(points_normals)
+    cc = pc if centers_coords is None else _f(centers_coords)
+    cn = pn if centers_normals is None else _f(centers_normals)
+    nb = _i(neighbors)
+    B, M, U = nb.shape
+    gi = np.broadcast_to(nb.reshape(B, 1, M * U), (B, 3, M * U))
+    q = np.take_along_axis(pc, gi, 2).reshape(B, 3, M, U)            # F.grouping(points_coords, idx)
+    r = np.take_along_axis(pn, gi, 2).reshape(B, 3, M, U)
+    c = cc[:, :, :, None]; n = cn[:, :, :, None]
+    rel = (q - c).astype(f32)                                        # ball_query.py:24
+    d = (c - rel).astype(f32)                                        # pvcnn_classify.py:262
+    sq = (d * d).astype(f32)
+    dn = np.sqrt(((sq[:, 0] + sq[:, 1]).astype(f32) + sq[:, 2]).astype(f32)).astype(f32)      # :263
+    with np.errstate(divide="ignore", invalid="ignore"):
+        du = (d / dn[:, None]).astype(f32)                           # :264
+        dot = lambda a, b: (((a[:, 0] * b[:, 0]).astype(f32) + (a[:, 1] * b[:, 1]).astype(f32)).astype(f32)
+                            + (a[:, 2] * b[:, 2]).astype(f32)).astype(f32)
+        nb_ = np.broadcast_to(n, r.shape)
+        ac = lambda x: np.arccos(np.clip(x, f32(-1), f32(1))).astype(f32)
+        out = np.stack([ac(dot(r, du)), ac(dot(nb_, du)), ac(dot(r, nb_)), dn], 1)           # [B,4,M,U]  (:265-268)
+    return np.ascontiguousarray(out.transpose(0, 1, 3, 2))           # (b, 4, k, m)

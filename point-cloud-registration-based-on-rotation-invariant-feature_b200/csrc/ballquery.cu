@@ -159,6 +159,99 @@ extern "C" int ri_ball_query_f32(const float* centers, const float* points, int 
     return RI_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Local point-pair features of the shipped models, straight from the neighbour indices.
+// Replaces the torch block of PVCNN_classifier.forward, with_local_feat == 'ppf' (/root/reference/PVCNN/models/
+// pvcnn_classify.py:252-270) together with the BallQuery module's grouping (PVCNN/modules/ball_query.py:16-35), which
+// materialise the grouped coordinates + normals [B,6,U,M] (100 MB at B = 32, U = 128, M = 1024), their expansions and six
+// element-wise / reduction passes over them.  Arithmetic kept operation for operation (all fp32, no contraction):
+//   rel  = p_nbr - c                                  (ball_query.py:24 — the grouper returns RELATIVE coordinates)
+//   d    = c - rel                                    (:262 — so d = 2c - p_nbr: the shipped weights were trained on this)
+//   dn   = sqrt((d0^2 + d1^2) + d2^2)                 (:263 torch.norm(dim=1))
+//   du   = d / dn                                     (:264 — no epsilon: dn = 0 gives NaN, as in torch)
+//   out  = acos(clamp(<n_nbr, du>)), acos(clamp(<n_c, du>)), acos(clamp(<n_nbr, n_c>)), dn      (:265-268)
+// with every dot product as torch's mul + sum(dim=1): three rounded products, then (p0 + p1) + p2; acosf is the same
+// libdevice function torch calls.  out [B,4,U,M] (the reference's (b, 4, k, m)), written coalesced along M: the index tile
+// of 32 centres is transposed through shared memory (indices are [B,M,U], U innermost).
+constexpr int kLpThreads = 256;
+constexpr int kLpCentres = 32;
+
+__device__ __forceinline__ float lp_dot(float a0, float a1, float a2, float b0, float b1, float b2)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1)), __fmul_rn(a2, b2));
+}
+__device__ __forceinline__ float lp_acos_clamped(float x)
+{
+    // torch.clamp propagates NaN; fminf/fmaxf would swallow it
+    const float c = (x != x) ? x : fminf(fmaxf(x, -1.0f), 1.0f);
+    return acosf(c);
+}
+
+__global__ void __launch_bounds__(kLpThreads)
+local_ppf_kernel(const float* __restrict__ pc, const float* __restrict__ pn, const float* __restrict__ cc,
+                 const float* __restrict__ cn, const int* __restrict__ nbr, int N, int M, int U, float* __restrict__ out)
+{
+    extern __shared__ int lp_tile[];                               // [kLpCentres][U + 1]
+    const int b = blockIdx.y;
+    const int m0 = blockIdx.x * kLpCentres;
+    const int mc = min(kLpCentres, M - m0);
+    const int ld = U + 1;
+    const int* I = nbr + ((size_t)b * M + m0) * U;
+    for (int e = threadIdx.x; e < mc * U; e += kLpThreads) {       // coalesced along U
+        const int ml = e / U, u = e - ml * U;
+        lp_tile[ml * ld + u] = I[e];
+    }
+    __syncthreads();
+    const float* PC = pc + (size_t)b * 3 * N;
+    const float* PN = pn + (size_t)b * 3 * N;
+    const float* CC = cc + (size_t)b * 3 * M;
+    const float* CN = cn + (size_t)b * 3 * M;
+    const size_t um = (size_t)U * M;
+    float* O = out + (size_t)b * 4 * um;
+    for (int e = threadIdx.x; e < kLpCentres * U; e += kLpThreads) {
+        const int ml = e & (kLpCentres - 1), u = e >> 5;           // lanes walk the centres: coalesced stores
+        if (ml >= mc) continue;
+        const int m = m0 + ml;
+        int j = lp_tile[ml * ld + u];
+        j = j < 0 ? 0 : (j >= N ? N - 1 : j);
+        const float c0 = CC[m], c1 = CC[m + M], c2 = CC[m + 2 * (size_t)M];
+        const float n0 = CN[m], n1 = CN[m + M], n2 = CN[m + 2 * (size_t)M];
+        const float q0 = __ldg(PC + j), q1 = __ldg(PC + j + N), q2 = __ldg(PC + j + 2 * (size_t)N);
+        const float r0 = __ldg(PN + j), r1 = __ldg(PN + j + N), r2 = __ldg(PN + j + 2 * (size_t)N);
+        const float d0 = __fsub_rn(c0, __fsub_rn(q0, c0)), d1 = __fsub_rn(c1, __fsub_rn(q1, c1)), d2 = __fsub_rn(c2, __fsub_rn(q2, c2));
+        const float dn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)));
+        const float u0 = __fdiv_rn(d0, dn), u1 = __fdiv_rn(d1, dn), u2 = __fdiv_rn(d2, dn);
+        const size_t o = (size_t)u * M + m;
+        O[o] = lp_acos_clamped(lp_dot(r0, r1, r2, u0, u1, u2));
+        O[um + o] = lp_acos_clamped(lp_dot(n0, n1, n2, u0, u1, u2));
+        O[2 * um + o] = lp_acos_clamped(lp_dot(r0, r1, r2, n0, n1, n2));
+        O[3 * um + o] = dn;
+    }
+}
+
+// points_coords / points_normals [B,3,N], centers_coords / centers_normals [B,3,M], neighbors [B,M,U] (ri_ball_query_f32)
+// -> out [B,4,U,M]
+extern "C" int ri_local_ppf_f32(const float* points_coords, const float* points_normals, const float* centers_coords,
+                                const float* centers_normals, const int* neighbors, int B, int N, int M, int U,
+                                float* out, void* stream)
+{
+    if (B < 0 || N < 0 || M < 0 || U < 0) return RI_ERR_BAD_ARG;
+    if (B > 65535) return RI_ERR_UNSUPPORTED;
+    if (B == 0 || M == 0 || U == 0) return RI_OK;
+    if (N == 0) return RI_ERR_BAD_ARG;
+    const size_t smem = (size_t)kLpCentres * (U + 1) * sizeof(int);
+    if (smem > 200 * 1024) return RI_ERR_UNSUPPORTED;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(local_ppf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    dim3 grid((M + kLpCentres - 1) / kLpCentres, B);
+    local_ppf_kernel<<<grid, kLpThreads, smem, (cudaStream_t)stream>>>(points_coords, points_normals, centers_coords,
+                                                                      centers_normals, neighbors, N, M, U, out);
+    RI_LAUNCH_CHECK();
+    return RI_OK;
+}
+
 // grouping_forward (grouping/grouping.cpp): feat [B,C,N], idx [B,M,U] -> out [B,C,M,U] (fully overwritten)
 extern "C" int ri_grouping_f32(const float* feat, const int* idx, int B, int C, int N, int M, int U, float* out, void* stream)
 {

@@ -4,7 +4,7 @@ import torch
 
 from ..backend import _backend
 
-__all__ = ['ball_query', 'grouping']
+__all__ = ['ball_query', 'grouping', 'local_ppf', 'ball_local_ppf']
 
 
 def ball_query(centers_coords, points_coords, radius, num_neighbors):
@@ -31,3 +31,21 @@ class Grouping(torch.autograd.Function):
 
 
 grouping = Grouping.apply
+
+
+def local_ppf(points_coords, points_normals, neighbor_indices, centers_coords=None, centers_normals=None):
+    """The `with_local_feat == 'ppf'` features of the shipped models (/root/reference/PVCNN/models/pvcnn_classify.py:252-270)
+    straight from the ball-query indices, one kernel, nothing grouped in memory: FloatTensor[B,4,U,M] =
+    (angle(n_nbr, d), angle(n_centre, d), angle(n_nbr, n_centre), |d|) with the reference's d = c - (p_nbr - c).
+    Centres default to the points themselves (what the models do: `center_coords = coords`)."""
+    cc = points_coords if centers_coords is None else centers_coords
+    cn = points_normals if centers_normals is None else centers_normals
+    return torch.ops.ri.local_ppf(points_coords.float().contiguous(), points_normals.float().contiguous(),
+                                  cc.float().contiguous(), cn.float().contiguous(), neighbor_indices.contiguous())
+
+
+def ball_local_ppf(coords, normals, radius=0.3, num_neighbors=128):
+    """ball query (self excluded, first `num_neighbors` in index order) + local_ppf: what BallQuery + the torch PPF block compute
+    for `neighbor_num=128, radius=0.3` (pvcnn_classify.py:61-63)."""
+    idx = ball_query(coords, coords, radius, num_neighbors)
+    return local_ppf(coords, normals, idx)

@@ -601,3 +601,29 @@ def lrf_change_coords(coords: torch.Tensor, mean: torch.Tensor) -> tuple[torch.T
 def _(coords, mean):
     B, _, N = coords.shape
     return coords.new_empty((B, 3, N)), coords.new_empty((B, 3, 3)), coords.new_empty((B,), dtype=torch.int32)
+
+
+# ---------------------------------------------------------------------------------------------- local PPF (f1, fused)
+@torch.library.custom_op("ri::local_ppf", mutates_args=())
+def local_ppf(points_coords: torch.Tensor, points_normals: torch.Tensor, centers_coords: torch.Tensor,
+              centers_normals: torch.Tensor, neighbors: torch.Tensor) -> torch.Tensor:
+    """points_* [B,3,N], centers_* [B,3,M] f32, neighbors [B,M,U] i32 -> [B,4,U,M] (pvcnn_classify.py:252-270)."""
+    for t, n in ((points_coords, "points_coords"), (points_normals, "points_normals"), (centers_coords, "centers_coords"),
+                 (centers_normals, "centers_normals")):
+        _req(t, n, torch.float32)
+    _req(neighbors, "neighbors", torch.int32)
+    dev = _same_device(points_coords, points_normals, centers_coords, centers_normals, neighbors)
+    B, _, N = points_coords.shape
+    M = centers_coords.shape[2]
+    U = neighbors.shape[2]
+    with torch.cuda.device(dev):
+        out = torch.empty((B, 4, U, M), dtype=torch.float32, device=dev)
+        _check(_L.ri_local_ppf_f32(points_coords.data_ptr(), points_normals.data_ptr(), centers_coords.data_ptr(),
+                                   centers_normals.data_ptr(), neighbors.data_ptr(), B, N, M, U, out.data_ptr(), _stream()),
+               "ri_local_ppf")
+    return out
+
+
+@local_ppf.register_fake
+def _(points_coords, points_normals, centers_coords, centers_normals, neighbors):
+    return points_coords.new_empty((points_coords.shape[0], 4, neighbors.shape[2], centers_coords.shape[2]))

@@ -79,3 +79,50 @@ def test_ball_query_errors(ri):
         torch.ops.ri.ball_query(x.cpu(), x, 0.3, 4)
     with pytest.raises(RuntimeError):
         torch.ops.ri.grouping(x, torch.zeros(1, 4, 4, device="cuda", dtype=torch.int64))
+
+
+def _torch_local_ppf(inputs, grouper, neighbor_num):
+    """The reference's own torch operations (pvcnn_classify.py:252-269), run on the GPU through the BallQuery module mirror."""
+    coords = inputs[:, :3, :]
+    normals = inputs[:, 3:6, :]
+    center_coords = coords
+    center_normals = normals
+    neighbor_coords_normals = grouper(coords, center_coords, normals)
+    neighbor_coords = neighbor_coords_normals[:, :3, :, :]
+    neighbor_normals = neighbor_coords_normals[:, 3:, :, :]
+    center_coords_k_repeat = center_coords.unsqueeze(2).expand(-1, -1, neighbor_num, -1)
+    center_normals_k_repeat = center_normals.unsqueeze(2).expand(-1, -1, neighbor_num, -1)
+    d = center_coords_k_repeat - neighbor_coords
+    d_norm = torch.norm(d, dim=1, p=2, keepdim=True)
+    d_unit = d / d_norm
+    nr_d = torch.acos(neighbor_normals.mul(d_unit).sum(dim=1, keepdim=True).clamp(-1, 1))
+    ni_d = torch.acos(center_normals_k_repeat.mul(d_unit).sum(dim=1, keepdim=True).clamp(-1, 1))
+    nr_ni = torch.acos(neighbor_normals.mul(center_normals_k_repeat).sum(dim=1, keepdim=True).clamp(-1, 1))
+    return torch.cat((nr_d, ni_d, nr_ni, d_norm), dim=1)
+
+
+@pytest.mark.parametrize("B,N,U,radius", [(32, 1024, 128, 0.3), (3, 500, 16, 0.25), (2, 1000, 7, 0.5)])
+def test_local_ppf_fused_equals_reference_torch_ops(oracle, B, N, U, radius):
+    """One kernel from the neighbour indices == BallQuery grouping + the reference's torch PPF block, on the same device.
+    Angles where |cos| is within 1e-4 of 1 are compared loosely (acos is ill-conditioned there and torch's reduction kernels
+    may contract differently); everything else to 2e-6; |d| bit for bit."""
+    import ri_b200
+    from ri_b200 import synth
+    pts = torch.from_numpy(synth.make_clouds(B, N, seed=31)).cuda()
+    pts[:, 3:6] = torch.nn.functional.normalize(pts[:, 3:6], dim=1)
+    grouper = ri_b200.modules.BallQuery(radius, U, include_coordinates=True)
+    want = _torch_local_ppf(pts, grouper, U)
+    got = ri_b200.functional.ball_local_ppf(pts[:, :3].contiguous(), pts[:, 3:6].contiguous(), radius, U)
+    assert got.shape == want.shape == (B, 4, U, N)
+    assert torch.equal(got[:, 3], want[:, 3]), "|d| differs"
+    err = (got[:, :3] - want[:, :3]).abs()
+    edge = (torch.cos(want[:, :3]).abs() > 1 - 1e-4)
+    assert float(err[~edge].max()) <= 2e-6
+    assert float(err[edge].max() if edge.any() else 0.0) <= 2e-3
+    # C oracle-level restatement in numpy (glibc acosf: 1-2 ulp from libdevice)
+    idx = ri_b200.functional.ball_query(pts[:, :3].contiguous(), pts[:, :3].contiguous(), radius, U)
+    o = oracle.local_ppf(pts[:, :3].cpu().numpy(), pts[:, 3:6].cpu().numpy(), idx.cpu().numpy())
+    oerr = np.abs(got.cpu().numpy() - o)
+    oedge = np.abs(np.cos(o[:, :3])) > 1 - 1e-4
+    assert np.array_equal(got[:, 3].cpu().numpy(), o[:, 3])
+    assert oerr[:, :3][~oedge].max() <= 2e-6

@@ -33,3 +33,24 @@ try:
     assert torch.equal(ref.ball_query(pts, pts, R, U), idx)
 except Exception as ex:
     print("reference backend unavailable:", ex)
+
+# the models' local PPF block: one kernel from the indices vs BallQuery grouping + the reference's torch ops (same GPU)
+import ri_b200
+nrm = torch.nn.functional.normalize(torch.randn(B, 3, N, device="cuda"), dim=1).contiguous()
+grouper = ri_b200.modules.BallQuery(R, U, include_coordinates=True)
+
+
+def torch_block():
+    g = grouper(pts, pts, nrm)
+    nc, nn_ = g[:, :3], g[:, 3:]
+    ck = pts.unsqueeze(2).expand(-1, -1, U, -1); nk = nrm.unsqueeze(2).expand(-1, -1, U, -1)
+    d = ck - nc
+    dn = torch.norm(d, dim=1, p=2, keepdim=True)
+    du = d / dn
+    return torch.cat((torch.acos(nn_.mul(du).sum(1, keepdim=True).clamp(-1, 1)), torch.acos(nk.mul(du).sum(1, keepdim=True).clamp(-1, 1)),
+                      torch.acos(nn_.mul(nk).sum(1, keepdim=True).clamp(-1, 1)), dn), 1)
+
+
+c = t(lambda: ri_b200.functional.ball_local_ppf(pts, nrm, R, U))
+d = t(torch_block, 5)
+print("local PPF [B,4,U,N] incl. ball query: fused %8.1f us   BallQuery module + torch ops %8.1f us   -> %.1fx" % (c, d, d / c))
