@@ -535,6 +535,15 @@ def test_lanes_match_serial_engine(ri, shape):
     for fe, w in zip(engines, want):
         for n, v in w.items():
             assert torch.equal(getattr(fe, n), v), n
+    # stress: 900 more steps in flight (persistent TMA kernels, mbarrier rings, dynamic work counters) — same bits at the end
+    lanes.begin()
+    for i in range(900):
+        lanes.forward(i)
+    lanes.end()
+    torch.cuda.synchronize()
+    for fe, w in zip(engines, want):
+        for n, v in w.items():
+            assert torch.equal(getattr(fe, n), v), "after 900 steps: " + n
 
 
 @pytest.mark.parametrize("k,n,m", [(20, 1024, 1024), (8, 100, 777), (16, 1000, 3000), (32, 333, 64), (20, 5, 3)])
