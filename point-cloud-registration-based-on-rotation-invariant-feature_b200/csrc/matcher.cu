@@ -242,7 +242,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 struct GemmSmem {                                            // after the stage ring
     unsigned long long colkey[4][kTileN];                    // per epilogue warp, per column
     float n2[kTileN];
-    unsigned long long raw[kStages], full[kStages], empty[kStages], acc_full[2], acc_empty[2];
+    unsigned long long raw[8], full[8], empty[8], acc_full[2], acc_empty[2];      // rings of up to 8 stages
     uint32_t tmem_base;
 };
 
@@ -482,6 +482,285 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
     }
 }
 
+// ------------------------------------------------------------------------------------------------ match_gemm_pair
+// The persistent kernel on a CTA PAIR (cluster of 2, tcgen05 cta_group::2).  The pair walks 256 x 256 tiles: each CTA owns 128
+// rows of f1 (its A tile, its 128 TMEM lanes in both accumulator buffers) and stages HALF of the f2 tile (128 rows of B); the
+// leader's single thread issues M256 N256 K8 MMAs and the hardware hands each SM the other half of B.  Per SM and stage the
+// shared-memory port then serves 16 KB of TMA writes + 32 KB of converter traffic + 48 KB of operand reads instead of
+// 24 + 48 + 72: the single-CTA main loop runs at the shared-memory roofline (1100 clk per stage for 888 clk of MMA work).
+//   raw[s]                 per CTA: its own TMA bytes
+//   full[s]                in the LEADER: 4 converter warps of each CTA (remote mbarrier.arrive through mapa)
+//   empty[s], acc_full[b]  in both CTAs, signalled by tcgen05.commit ... multicast::cluster (mask 0b11)
+//   acc_empty[b]           in the LEADER: the 8 epilogue warps of each CTA
+constexpr int kPairTileM = 256;
+constexpr int kHalfN = kTileN / 2;                           // rows of f2 staged per CTA
+constexpr int kB2Bytes = kHalfN * kRowBytes;                 // 8 KB (one plane)
+constexpr int kStage2Bytes = 2 * kABytes + 2 * kB2Bytes;     // 32 KB
+constexpr int kStagesP = 6;                                  // deeper ring: every stage hand-over crosses the pair twice
+constexpr int kConvGroupsP = 3;
+constexpr int kPThreadsP = 32 * (kEpiWarps + 4 * kConvGroupsP + 2);
+static_assert(kStagesP % kConvGroupsP == 0, "each stage must belong to one converter group");
+constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
+                             ((uint32_t)(kPairTileM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_wait_cl(uint32_t bar, uint32_t parity)      // acquire at cluster scope
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITC_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONEC_%=;\n"
+        "bra WAITC_%=;\n"
+        "DONEC_%=:\n"
+        "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreadsP, 1)
+match_gemm_pair_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
+                  const float* __restrict__ nrm1, const float* __restrict__ nrm2,
+                  int n1, int n2, int n1p, int n2p, int Cp, int tiles_m, int tiles_n, int total_tiles,
+                  unsigned long long* __restrict__ rowkey, unsigned long long* __restrict__ colkey,
+                  unsigned long long* __restrict__ dbg)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    GemmSmem* S = reinterpret_cast<GemmSmem*>(smem + (size_t)kStagesP * kStage2Bytes);
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = (int)blockIdx.x >> 1, nclusters = (int)gridDim.x >> 1;
+    // debug timeline (tools/exp_match_timeline.py): CTA 0 stamps %globaltimer at a few events of its first 8 tiles
+    auto stamp = [&](int it, int ev) {
+        if (dbg != nullptr && blockIdx.x == 0 && it < 8) {
+            unsigned long long tt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+            dbg[it * 8 + ev] = tt;
+        }
+    };
+    const uint32_t ring = ri_smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
+    const int nk = Cp / kChunkK;
+    // stage layout: [A hi 8 KB][A lo 8 KB][B hi 16 KB][B lo 16 KB]; the raw fp32 tiles land in the hi regions
+    constexpr int kAHi = 0, kALo = kABytes, kBHi = 2 * kABytes, kBLo = 2 * kABytes + kB2Bytes;
+    constexpr int kProdWarp = kConvWarp0 + 4 * kConvGroupsP, kMmaWarp = kProdWarp + 1;
+    const int my_tiles = (cluster_id < total_tiles) ? (total_tiles - cluster_id + nclusters - 1) / nclusters : 0;
+    auto decode = [&](int it, int& pair, int& m0, int& c0) {
+        const int tile = cluster_id + it * nclusters;                 // a 256 x 256 tile of the pair
+        const int per = tiles_m * tiles_n;
+        pair = tile / per;
+        const int rem = tile - pair * per;
+        m0 = (rem / tiles_n) * kPairTileM + (int)rank * kTileM;      // this CTA's 128 rows of f1
+        c0 = (rem - (rem / tiles_n) * tiles_n) * kTileN;
+    };
+
+    if (t == 0) {
+        for (int s = 0; s < kStagesP; ++s) {
+            mbar_init(ri_smem_u32(&S->raw[s]), 1);           // TMA producer's expect_tx arrival + the bytes
+            mbar_init(ri_smem_u32(&S->full[s]), 8);          // the owning group's 4 converter warps in each CTA (used in the leader)
+            mbar_init(ri_smem_u32(&S->empty[s]), 1);         // tcgen05.commit
+        }
+        for (int q = 0; q < 2; ++q) {
+            mbar_init(ri_smem_u32(&S->acc_full[q]), 1);      // tcgen05.commit after a tile's last MMA
+            mbar_init(ri_smem_u32(&S->acc_empty[q]), 2 * kEpiWarps);                 // both CTAs' epilogue warps (used in the leader)
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        ri_fence_proxy_async_smem();
+    }
+    if (warp == kMmaWarp) {                                  // TMEM: 2 x 256 fp32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(ri_smem_u32(&S->tmem_base)), "r"((uint32_t)(2 * kTileN)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                      // both CTAs' barriers exist before anything crosses the pair
+    tc_fence_after();
+    const uint32_t tmem = S->tmem_base;
+
+    if (warp == kProdWarp) {
+        if (lane == 0) {                                     // ---- TMA producer: raw fp32 tiles, 24 KB per stage
+            const size_t planeA = (size_t)n1p * kRowBytes, planeB = (size_t)n2p * kRowBytes;
+            int g = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                int pair, m0, c0;
+                decode(it, pair, m0, c0);
+                const uint8_t* A = reinterpret_cast<const uint8_t*>(img1) + (size_t)pair * n1p * Cp * 4;
+                const uint8_t* B = reinterpret_cast<const uint8_t*>(img2) + (size_t)pair * n2p * Cp * 4;
+                for (int kc = 0; kc < nk; ++kc, ++g) {
+                    const int s = g % kStagesP;
+                    const uint32_t ph = (g / kStagesP) & 1;
+                    mbar_wait_cl(ri_smem_u32(&S->empty[s]), ph ^ 1);
+                    const uint32_t bar = ri_smem_u32(&S->raw[s]);
+                    mbar_expect_tx(bar, kABytes + kB2Bytes);
+                    const uint32_t dst = ring + s * kStage2Bytes;
+                    bulk_g2s(dst + kAHi, A + (size_t)kc * planeA + (size_t)m0 * kRowBytes, kABytes, bar);
+                    bulk_g2s(dst + kBHi, B + (size_t)kc * planeB + (size_t)(c0 + (int)rank * kHalfN) * kRowBytes, kB2Bytes, bar);
+                }
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        if (lane == 0 && rank == 0) {                        // ---- MMA issuer: the leader CTA only
+            int g = 0;
+            for (int it = 0; it < my_tiles; ++it) {
+                const int buf = it & 1;
+                stamp(it, 0);
+                mbar_wait_cl(ri_smem_u32(&S->acc_empty[buf]), ((it >> 1) & 1) ^ 1);     // the epilogue has drained this buffer
+                tc_fence_after();
+                stamp(it, 1);
+                const uint32_t acc = tmem + (uint32_t)(buf * kTileN);
+                for (int kc = 0; kc < nk; ++kc, ++g) {
+                    const int s = g % kStagesP;
+                    const uint32_t ph = (g / kStagesP) & 1;
+                    mbar_wait_cl(ri_smem_u32(&S->full[s]), ph);
+                    tc_fence_after();
+                    const uint32_t base = ring + s * kStage2Bytes;
+#pragma unroll
+                    for (int ks = 0; ks < kChunkK / 8; ++ks) {
+                        const uint32_t koff = ks * 2 * kLBO;     // one K-step = two 16-byte k-cores
+                        const uint64_t a_hi = smem_desc(base + kAHi + koff), a_lo = smem_desc(base + kALo + koff);
+                        const uint64_t b_hi = smem_desc(base + kBHi + koff), b_lo = smem_desc(base + kBLo + koff);
+                        tc_mma2_tf32(acc, a_lo, b_hi, kIdesc2, (kc | ks) != 0);    // small terms first
+                        tc_mma2_tf32(acc, a_hi, b_lo, kIdesc2, 1);
+                        tc_mma2_tf32(acc, a_hi, b_hi, kIdesc2, 1);
+                    }
+                    tc_commit2(ri_smem_u32(&S->empty[s]));       // stage reusable in BOTH CTAs once these MMAs have read it
+                }
+                tc_commit2(ri_smem_u32(&S->acc_full[buf]));      // this tile's accumulators are complete in both CTAs
+                stamp(it, 2);
+            }
+        }
+    } else if (warp >= kConvWarp0) {
+        // ---- converters: thread tg of a group splits A-tile row tg and B-tile rows tg, tg + 128 (4 k-core slots each) of
+        //      the group's stages.  One stage is a serial chain for its four warps (wait -> 12 LDS -> split -> 12 STS ->
+        //      proxy fence -> arrive, ~2.4k clk against 888 clk of MMA work): with a single group the tensor pipe waited
+        //      on it (31 % busy); kConvGroupsP groups convert that many stages at the same time.
+        const int ct = t - kConvWarp0 * 32;
+        const int grp = ct >> 7, tg = ct & 127;
+        const uint32_t slot_a = (uint32_t)(tg >> 3) * kSBO + (uint32_t)(tg & 7) * 16;      // row tg inside a plane
+        const uint32_t full_leader = mapa_shared(ri_smem_u32(&S->full[0]), 0);
+        const int total = my_tiles * nk;
+        for (int g = grp; g < total; g += kConvGroupsP) {
+            const int s = g % kStagesP;
+            const uint32_t ph = (g / kStagesP) & 1;
+            mbar_wait(ri_smem_u32(&S->raw[s]), ph);
+            uint8_t* st = smem + (size_t)s * kStage2Bytes;
+            float4 v[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                v[2 * q + 0] = *reinterpret_cast<const float4*>(st + kAHi + slot_a + q * kLBO);
+                v[2 * q + 1] = *reinterpret_cast<const float4*>(st + kBHi + slot_a + q * kLBO);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 h, l;
+                split4(v[2 * q + 0], h, l);
+                if (kWriteHi) *reinterpret_cast<float4*>(st + kAHi + slot_a + q * kLBO) = h;
+                *reinterpret_cast<float4*>(st + kALo + slot_a + q * kLBO) = l;
+                split4(v[2 * q + 1], h, l);
+                if (kWriteHi) *reinterpret_cast<float4*>(st + kBHi + slot_a + q * kLBO) = h;
+                *reinterpret_cast<float4*>(st + kBLo + slot_a + q * kLBO) = l;
+            }
+            ri_fence_proxy_async_smem();                     // generic-proxy stores -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(full_leader + (uint32_t)s * 8u);
+        }
+    } else {
+        // ---- epilogue warps: warp w reads TMEM lanes [32 (w % 4), +32) = tile rows, columns [128 (w / 4), +128)
+        const int wq = warp & 3, half = warp >> 2, tr = t & 127;
+        const uint32_t acc_empty_leader = mapa_shared(ri_smem_u32(&S->acc_empty[0]), 0);
+        constexpr int kColsPerHalf = kTileN / (kEpiWarps / 4);
+        for (int it = 0; it < my_tiles; ++it) {
+            int pair, m0, c0;
+            decode(it, pair, m0, c0);
+            const int buf = it & 1;
+            for (int j = t; j < kTileN; j += 32 * kEpiWarps) S->n2[j] = nrm2[(size_t)pair * n2p + c0 + j];
+            const int gi = m0 + tr;
+            const bool row_ok = gi < n1;
+            const float na = nrm1[(size_t)pair * n1p + gi];
+            asm volatile("bar.sync 1, %0;" :: "n"(32 * kEpiWarps) : "memory");        // n2 staged; previous tile's colkey consumed
+            if (t == 0) stamp(it, 3);
+            mbar_wait_cl(ri_smem_u32(&S->acc_full[buf]), (it >> 1) & 1);
+            tc_fence_after();
+            if (t == 0) stamp(it, 4);
+            float best = 0.f; int best_j = -1;
+            for (int cc = half * kColsPerHalf; cc < (half + 1) * kColsPerHalf; cc += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * kTileN + cc), v);
+                unsigned long long mine = ~0ull;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int j = c0 + cc + e;
+                    const float d = __fmaf_rn(-2.0f, __uint_as_float(v[e]), __fadd_rn(na, S->n2[cc + e]));
+                    if (j < n2 && (best_j < 0 || d < best)) { best = d; best_j = j; }
+                    const unsigned key = row_ok ? ordered_u32(d) : 0xffffffffu;
+                    const unsigned mn = __reduce_min_sync(0xffffffffu, key);
+                    const unsigned who = __ballot_sync(0xffffffffu, key == mn);
+                    if (lane == e)
+                        mine = ((unsigned long long)mn << 32) | (unsigned)(m0 + wq * 32 + (__ffs(who) - 1));
+                }
+                S->colkey[wq][cc + lane] = mine;
+            }
+            // the accumulator buffer has been read: hand it back to the MMA issuer before the (slow) global atomics
+            tc_fence_before();
+            __syncwarp();
+            if (t == 0) stamp(it, 5);
+            if (lane == 0) mbar_arrive_remote(acc_empty_leader + (uint32_t)buf * 8u);
+            if (row_ok && best_j >= 0)
+                atomicMin(rowkey + (size_t)pair * n1p + gi, ((unsigned long long)ordered_u32(best) << 32) | (unsigned)best_j);
+            asm volatile("bar.sync 1, %0;" :: "n"(32 * kEpiWarps) : "memory");        // all column keys are in smem
+            for (int j = t; j < kTileN; j += 32 * kEpiWarps) {
+                if (c0 + j >= n2) continue;
+                unsigned long long k0 = S->colkey[0][j];
+                const unsigned long long k1 = S->colkey[1][j], k2 = S->colkey[2][j], k3 = S->colkey[3][j];
+                k0 = k1 < k0 ? k1 : k0; k0 = k2 < k0 ? k2 : k0; k0 = k3 < k0 ? k3 : k0;
+                if ((unsigned)(k0 >> 32) != 0xffffffffu) atomicMin(colkey + (size_t)pair * n2p + c0 + j, k0);
+            }
+            if (t == 0) stamp(it, 6);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                      // neither CTA leaves (or frees TMEM) while the other may still use it
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)(2 * kTileN)) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ match_finish
 // Two kernels.  match_dist: one thread per row of every pair — corr12[i] = argmin_j, the mutual flag, and dist12[i] =
 // |f1_i - f2_corr12[i]|^2 accumulated in fp32 from the re-tiled descriptors (per 16-channel chunk a row is 4 x 16 B at a
@@ -604,9 +883,25 @@ extern "C" int ri_mutual_nn_tf32x3(const float* desc1, const float* desc2, int P
         const long long total = (long long)P * tiles_m * tiles_n;
         if (total > 0x7fffffffLL) return RI_ERR_UNSUPPORTED;
         const int grid = total < ri_num_sms() ? (int)total : ri_num_sms();
-        match_gemm_kernel<<<grid, kPThreads, smem, st>>>(img1, img2, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp, tiles_m, tiles_n,
-                                                         (int)total, rowkey, colkey,
-                                                         reinterpret_cast<unsigned long long*>(getenv("RI_MATCH_DBG") ? ws + L.mutual : nullptr));
+        unsigned long long* dbg = reinterpret_cast<unsigned long long*>(getenv("RI_MATCH_DBG") ? ws + L.mutual : nullptr);
+        // default: CTA pairs (cta_group::2) when a pair tile is not mostly padding; RI_MATCH_PAIR=0 / 1 forces a form
+        const char* pev = getenv("RI_MATCH_PAIR");
+        const bool pair_form = pev ? atoi(pev) == 1 : (n1 > kTileM && ri_num_sms() >= 2);
+        if (pair_form) {
+            // CTA pairs over 256 x 256 tiles (cta_group::2)
+            const size_t smem2 = (size_t)kStagesP * kStage2Bytes + sizeof(GemmSmem) + 1024;
+            e = cudaFuncSetAttribute(match_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            if (e != cudaSuccess) return (int)e;
+            const int ptiles_m = (n1 + kPairTileM - 1) / kPairTileM;
+            const long long ptotal = (long long)P * ptiles_m * tiles_n;
+            int clusters = ri_num_sms() / 2;
+            if (ptotal < clusters) clusters = (int)ptotal;
+            match_gemm_pair_kernel<<<2 * clusters, kPThreadsP, smem2, st>>>(img1, img2, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp,
+                                                                          ptiles_m, tiles_n, (int)ptotal, rowkey, colkey, dbg);
+        } else {
+            match_gemm_kernel<<<grid, kPThreads, smem, st>>>(img1, img2, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp, tiles_m, tiles_n,
+                                                             (int)total, rowkey, colkey, dbg);
+        }
         RI_LAUNCH_CHECK();
         if (getenv("RI_MATCH_DBG")) return RI_OK;            // debug: keep the stamps (match_dist would overwrite them)
     }

@@ -180,3 +180,29 @@ def test_persistent_gemm_stress_two_streams():
         for mm in mms:
             assert torch.equal(mm.corr12, want[0]) and torch.equal(mm.corr21, want[1])
             assert torch.equal(mm.dist12, want[2]) and torch.equal(mm.count, want[3])
+
+
+@pytest.mark.parametrize("P,C,n1,n2,pm", [(3, 512, 1024, 1024, False), (2, 100, 300, 700, False), (2, 33, 1000, 130, True), (4, 64, 128, 256, False)])
+def test_pair_and_single_cta_forms_agree(P, C, n1, n2, pm):
+    """The two persistent GEMM forms (CTA pair with cta_group::2 over 256 x 256 tiles; single CTA over 128 x 256 tiles) return the
+    same argmins, matches and distances."""
+    import os
+    import ri_b200
+    g = torch.Generator(device="cuda"); g.manual_seed(C + n1)
+    shape1, shape2 = ((P, n1, C), (P, n2, C)) if pm else ((P, C, n1), (P, C, n2))
+    d1 = torch.randn(shape1, device="cuda", generator=g); d2 = torch.randn(shape2, device="cuda", generator=g)
+    res = {}
+    prev = os.environ.get("RI_MATCH_PAIR")
+    try:
+        for mode in ("0", "1"):
+            os.environ["RI_MATCH_PAIR"] = mode
+            r = ri_b200.matcher.mutual_nn(d1, d2, point_major=pm)
+            torch.cuda.synchronize()
+            res[mode] = {k: v.clone() for k, v in r.items()}
+    finally:
+        if prev is None:
+            os.environ.pop("RI_MATCH_PAIR", None)
+        else:
+            os.environ["RI_MATCH_PAIR"] = prev
+    for k in res["0"]:
+        assert torch.equal(res["0"][k], res["1"][k]), k
