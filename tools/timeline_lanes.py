@@ -53,18 +53,19 @@ class Traced(ri_b200.FrontEnd):
 
 
 fes = []
-for q in range(NL):
-    fe = Traced(B, N, C, k=k, r=r, voxel_shape="cube")
+for q in range(2 * NL):                      # the second half is not traced: it keeps the machine busy after the traced steps
+    cls = Traced if q < NL else ri_b200.FrontEnd
+    fe = cls(B, N, C, k=k, r=r, voxel_shape="cube")
     fe.load(synth.make_clouds(B, N, seed=q), synth.make_features(B, C, N, seed=q)); fes.append(fe)
 ln = ri_b200.FrontEndLanes(fes, lanes=NL)
 torch.cuda.synchronize()
 ln.begin()
-for i in range(8 * NL):
+for i in range(8 * 2 * NL):
     ln.forward(i)
 ln.end()
 torch.cuda.synchronize()
 rows = []
-for e, fe in enumerate(fes):
+for e, fe in enumerate(fes[:NL]):
     t = fe.stamps.cpu().numpy()[:len(fe.names)]
     d = dict(zip(fe.names, t))
     for kname in ("mean ", "front", "knn  ", "ppf  ", "fill ", "devox"):
