@@ -238,6 +238,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Column minima of a 32-row x 16-column block held one row per lane (x[c] = this lane's key of column c), by a butterfly:
+// at offset 16 / 8 / 4 / 2 a lane keeps the half of its columns selected by that bit of its lane id, hands the other half to
+// its partner and takes the minimum with what it receives; the last step folds the lane pair.  Afterwards lanes 2c and 2c + 1
+// both hold the minimum of column c.  16 exchanges of 64-bit keys per 16 columns, no warp-wide reduction instructions: the
+// redux.sync + ballot per element this replaces made the epilogue (16 us per tile) the kernel's bottleneck.
+__device__ __forceinline__ unsigned long long col_min16(unsigned long long (&x)[16], int lane)
+{
+#pragma unroll
+    for (int half = 8; half >= 1; half >>= 1) {
+        const bool up = (lane & (half << 1)) != 0;          // offsets 16, 8, 4, 2 for half = 8, 4, 2, 1
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const unsigned long long send = up ? x[i] : x[i + half];
+            const unsigned long long keep = up ? x[i + half] : x[i];
+            const unsigned long long got = __shfl_xor_sync(0xffffffffu, send, half << 1);
+            x[i] = got < keep ? got : keep;
+        }
+    }
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, x[0], 1);
+    return other < x[0] ? other : x[0];
+}
+
 // ------------------------------------------------------------------------------------------------ match_gemm
 struct GemmSmem {                                            // after the stage ring
     unsigned long long colkey[4][kTileN];                    // per epilogue warp, per column
@@ -441,19 +463,23 @@ match_gemm_kernel(const float* __restrict__ img1, const float* __restrict__ img2
             for (int cc = half * kColsPerHalf; cc < (half + 1) * kColsPerHalf; cc += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * kTileN + cc), v);
-                unsigned long long mine = ~0ull;
+                // row argmin in registers; column argmin of the 32 rows x 32 columns block by a shuffle butterfly over packed
+                // (ordered distance, row) keys, 16 columns at a time (col_min16): lowest row wins ties, as np.argmin
+                const unsigned rowid = (unsigned)(m0 + wq * 32 + lane);
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int j = c0 + cc + e;
-                    const float d = __fmaf_rn(-2.0f, __uint_as_float(v[e]), __fadd_rn(na, S->n2[cc + e]));
-                    if (j < n2 && (best_j < 0 || d < best)) { best = d; best_j = j; }
-                    const unsigned key = row_ok ? ordered_u32(d) : 0xffffffffu;
-                    const unsigned mn = __reduce_min_sync(0xffffffffu, key);
-                    const unsigned who = __ballot_sync(0xffffffffu, key == mn);
-                    if (lane == e)
-                        mine = ((unsigned long long)mn << 32) | (unsigned)(m0 + wq * 32 + (__ffs(who) - 1));
+                for (int hc = 0; hc < 2; ++hc) {
+                    unsigned long long x[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int ce = hc * 16 + e;
+                        const int j = c0 + cc + ce;
+                        const float d = __fmaf_rn(-2.0f, __uint_as_float(v[ce]), __fadd_rn(na, S->n2[cc + ce]));
+                        if (j < n2 && (best_j < 0 || d < best)) { best = d; best_j = j; }
+                        x[e] = ((unsigned long long)(row_ok ? ordered_u32(d) : 0xffffffffu) << 32) | rowid;
+                    }
+                    const unsigned long long mn = col_min16(x, lane);
+                    if ((lane & 1) == 0) S->colkey[wq][cc + hc * 16 + (lane >> 1)] = mn;
                 }
-                S->colkey[wq][cc + lane] = mine;
             }
             // the accumulator buffer has been read: hand it back to the MMA issuer before the (slow) global atomics
             tc_fence_before();
@@ -720,19 +746,23 @@ match_gemm_pair_kernel(const float* __restrict__ img1, const float* __restrict__
             for (int cc = half * kColsPerHalf; cc < (half + 1) * kColsPerHalf; cc += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * kTileN + cc), v);
-                unsigned long long mine = ~0ull;
+                // row argmin in registers; column argmin of the 32 rows x 32 columns block by a shuffle butterfly over packed
+                // (ordered distance, row) keys, 16 columns at a time (col_min16): lowest row wins ties, as np.argmin
+                const unsigned rowid = (unsigned)(m0 + wq * 32 + lane);
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const int j = c0 + cc + e;
-                    const float d = __fmaf_rn(-2.0f, __uint_as_float(v[e]), __fadd_rn(na, S->n2[cc + e]));
-                    if (j < n2 && (best_j < 0 || d < best)) { best = d; best_j = j; }
-                    const unsigned key = row_ok ? ordered_u32(d) : 0xffffffffu;
-                    const unsigned mn = __reduce_min_sync(0xffffffffu, key);
-                    const unsigned who = __ballot_sync(0xffffffffu, key == mn);
-                    if (lane == e)
-                        mine = ((unsigned long long)mn << 32) | (unsigned)(m0 + wq * 32 + (__ffs(who) - 1));
+                for (int hc = 0; hc < 2; ++hc) {
+                    unsigned long long x[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const int ce = hc * 16 + e;
+                        const int j = c0 + cc + ce;
+                        const float d = __fmaf_rn(-2.0f, __uint_as_float(v[ce]), __fadd_rn(na, S->n2[cc + ce]));
+                        if (j < n2 && (best_j < 0 || d < best)) { best = d; best_j = j; }
+                        x[e] = ((unsigned long long)(row_ok ? ordered_u32(d) : 0xffffffffu) << 32) | rowid;
+                    }
+                    const unsigned long long mn = col_min16(x, lane);
+                    if ((lane & 1) == 0) S->colkey[wq][cc + hc * 16 + (lane >> 1)] = mn;
                 }
-                S->colkey[wq][cc + lane] = mine;
             }
             // the accumulator buffer has been read: hand it back to the MMA issuer before the (slow) global atomics
             tc_fence_before();
