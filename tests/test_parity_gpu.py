@@ -319,8 +319,11 @@ def test_pvconv_forward_backward(ri):
         assert "coefficient" in keys and "voxel_layers.0.weight" in keys and "point_layers.layers.0.weight" in keys
 
 
-def test_frontend_engine_matches_ops(ri):
-    B, N, C, k, r = 8, 1024, 19, 20, 32
+@pytest.mark.parametrize("B,N,C,k,r", [(8, 1024, 19, 20, 32), (3, 2000, 5, 16, 16), (2, 1024, 4, 20, 64), (2, 600, 3, 8, 8),
+                                        (2, 5000, 3, 20, 32), (1, 1024, 9, 20, 22)])
+def test_frontend_engine_matches_ops(ri, B, N, C, k, r):
+    """The engine (one captured step) against the reference-shaped ops, on the fused-prefix path (N <= 1024), the phase-by-phase
+    path (N = 2000), the gather devoxelizer (r = 64), the k-NN hash grid + atomic voxelizer fallback (N = 5000) and an odd grid."""
     pts = clouds(B, N, 51); feats = ri.synth.make_features(B, C, N, 51)
     for shape in ("spherical", "cube"):
         fe = ri.FrontEnd(B, N, C, k=k, r=r, voxel_shape=shape)
@@ -336,10 +339,17 @@ def test_frontend_engine_matches_ops(ri):
         else:
             avg, ind, nc = ri.modules.Voxelization(r, normalize=False)(f, xyz)
             dv = ri.functional.trilinear_devoxelize(avg, nc, r)
-        assert torch.equal(dv.cpu(), res["devox"])
-        assert torch.equal(ri.functional.voxel_edge_features(avg, f, ind).cpu(), res["edge"])
-        again = fe(pts, feats)                           # graph replay is deterministic
-        assert all(torch.equal(again[kk], res[kk]) for kk in res)
+        edge = ri.functional.voxel_edge_features(avg, f, ind).cpu()
+        if N <= 4096:
+            assert torch.equal(dv.cpu(), res["devox"])
+            assert torch.equal(edge, res["edge"])
+            again = fe(pts, feats)                           # graph replay is deterministic
+            assert all(torch.equal(again[kk], res[kk]) for kk in res)
+        else:
+            # beyond the tiled path the voxelizer sums a cell with float atomics (as the reference does): the order, hence
+            # the last bits of the means, changes from run to run
+            assert scaled_err(A(dv), A(res["devox"])) <= TOL
+            assert scaled_err(A(edge), A(res["edge"])) <= TOL
 
 
 def test_error_behaviour(ri):
