@@ -32,6 +32,7 @@
 //   Fallback (N > 4096 points per cloud, r^3 not a multiple of 4, or misaligned pointers): memset + integer
 //   atomics for counts + float atomics for the means over a (point tile, channel group, cloud) grid.
 #include "ri_common.cuh"
+#include <cub/device/device_radix_sort.cuh>
 #include "prologue_math.cuh"
 #include <stdlib.h>
 
@@ -792,6 +793,186 @@ int vox_fill_launch(int B, int C, int N, int s, int b0, int b1, const VoxPlan& p
     return RI_OK;
 }
 
+// --------------------------------------------------------------------------------------- scan-sized clouds (N > 4096)
+// The same three phases — cell-sorted point list + occupied-cell table, compact cell means in ascending point order, dense
+// grid written once by vox_fill_kernel — for clouds that do not fit one CTA's shared-memory sort (ICL-NUIM-sized scans,
+// BASELINE configs[3]).  The (cloud, cell) keys of the whole batch go through ONE stable radix sort (cub::DeviceRadixSort,
+// library plumbing) of 32-bit keys  b * (s + 1) + cell  (cell = s for points outside the grid), the tables are rebuilt per
+// cloud by a block-wide head-flag scan, and the means are summed per (cell, channel) thread in sorted = ascending point
+// order: deterministic and equal to the oracle bit for bit, where the atomic path's float atomicAdd order changes from
+// run to run (the reference has the same property).
+constexpr int kLgThreads = 1024;
+
+template <bool SPH>
+__global__ void __launch_bounds__(256)
+vox_keys_large_kernel(const void* __restrict__ coords_v, int N, int r, int s, int* __restrict__ ind,
+                      unsigned* __restrict__ keys, int* __restrict__ vals)
+{
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    int cell;
+    if (SPH) {
+        const float* X = reinterpret_cast<const float*>(coords_v) + (size_t)b * 3 * N;
+        cell = ri_sph_cell(X[i], X[i + N], X[i + 2 * (size_t)N], r);
+    } else {
+        const int* X = reinterpret_cast<const int*>(coords_v) + (size_t)b * 3 * N;
+        cell = X[i] * r * r + X[i + N] * r + X[i + 2 * (size_t)N];                  // vox.cu:31
+    }
+    ind[(size_t)b * N + i] = cell;
+    const unsigned c = (cell >= 0 && cell < s) ? (unsigned)cell : (unsigned)s;
+    keys[(size_t)b * N + i] = (unsigned)b * (unsigned)(s + 1) + c;
+    vals[(size_t)b * N + i] = i;
+}
+
+// one CTA per cloud: sorted keys / point ids of the cloud -> the workspace tables of vox_ws_layout
+__global__ void __launch_bounds__(kLgThreads)
+vox_table_large_kernel(const unsigned* __restrict__ keys, const int* __restrict__ vals, int N, int s, int tile_cells, int ntiles,
+                       int* __restrict__ ws)
+{
+    __shared__ int swarp[kLgThreads / 32];
+    __shared__ int sbase[2];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const VoxWs L = vox_ws_layout(N, ntiles);
+    int* W = ws + (size_t)b * L.stride;
+    const unsigned* K = keys + (size_t)b * N;
+    const int* V = vals + (size_t)b * N;
+    const unsigned kbase = (unsigned)b * (unsigned)(s + 1);
+    const int E = (N + kLgThreads - 1) / kLgThreads;
+    const int u0 = tid * E;
+    int heads = 0, valid = 0;
+    for (int e = 0; e < E; ++e) {
+        const int u = u0 + e;
+        if (u < N) {
+            const unsigned c = K[u] - kbase;
+            if (c < (unsigned)s) { ++valid; if (u == 0 || K[u - 1] != K[u]) ++heads; }
+        }
+    }
+    // block-wide exclusive scan of heads, block-wide sum of valid
+    int incl = heads;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    int vs = valid;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, o);
+    if (lane == 31) swarp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        const int h = swarp[lane];
+        int hs = h;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, hs, o); if (lane >= o) hs += v; }
+        swarp[lane] = hs - h;
+        if (lane == 31) sbase[0] = hs;
+    }
+    __syncthreads();
+    int seg = swarp[wid] + (incl - heads);
+    const int U = sbase[0];
+    __syncthreads();
+    if (lane == 0) swarp[wid] = vs;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < kLgThreads / 32; ++w) t += swarp[w]; sbase[1] = t; }
+    __syncthreads();
+    const int nvalid = sbase[1];
+    for (int e = 0; e < E; ++e) {
+        const int u = u0 + e;
+        if (u < N) {
+            const int pt = V[u];
+            W[L.off_pid + u] = pt;
+            const unsigned c = K[u] - kbase;
+            if (c < (unsigned)s) {
+                if (u == 0 || K[u - 1] != K[u]) { W[L.off_cell + seg] = (int)c; W[L.off_start + seg] = u; ++seg; }
+                W[L.off_segof + pt] = seg - 1;
+            } else {
+                W[L.off_segof + pt] = -1;
+            }
+        }
+    }
+    if (tid == 0) { W[L.off_start + U] = nvalid; W[L.off_meta] = U; W[L.off_meta + 1] = nvalid; }
+    __syncthreads();                                             // off_cell complete (this CTA wrote all of it)
+    for (int t = tid; t <= ntiles; t += kLgThreads) {
+        const long long want = (long long)t * tile_cells;
+        int lo = 0, hi2 = U;
+        while (lo < hi2) {
+            const int mid = (lo + hi2) >> 1;
+            if ((long long)W[L.off_cell + mid] < want) lo = mid + 1; else hi2 = mid;
+        }
+        W[L.off_tile + t] = lo;
+    }
+}
+
+// one thread per occupied cell and channel group: sum f * (1/n) over the cell's points in ascending point order (vox.cu:61-72)
+constexpr int kLgChans = 4;
+__global__ void __launch_bounds__(256)
+vox_means_large_kernel(const float* __restrict__ feat, const int* __restrict__ ws, int C, int N, int ntiles, int ucap,
+                       float* __restrict__ means)
+{
+    const int b = blockIdx.z;
+    const VoxWs L = vox_ws_layout(N, ntiles);
+    const int* W = ws + (size_t)b * L.stride;
+    const int U = W[L.off_meta];
+    const int sg = blockIdx.x * 256 + threadIdx.x;
+    if (sg >= U) return;
+    const int c0 = blockIdx.y * kLgChans;
+    const int st = W[L.off_start + sg], cnt = W[L.off_start + sg + 1] - st;
+    const float inv = __fdiv_rn(1.0f, (float)cnt);                                   // vox.cu:66
+    const float* F = feat + (size_t)b * C * N;
+    float acc[kLgChans];
+#pragma unroll
+    for (int j = 0; j < kLgChans; ++j) acc[j] = 0.f;
+    for (int u = st; u < st + cnt; ++u) {
+        const int i = W[L.off_pid + u];
+#pragma unroll
+        for (int j = 0; j < kLgChans; ++j)
+            if (c0 + j < C) acc[j] = __fadd_rn(acc[j], __fmul_rn(__ldg(F + (size_t)(c0 + j) * N + i), inv));
+    }
+    float* M = means + (size_t)b * C * ucap;
+#pragma unroll
+    for (int j = 0; j < kLgChans; ++j)
+        if (c0 + j < C) M[(size_t)(c0 + j) * ucap + sg] = acc[j];
+}
+
+// edge [B,2C,N] from the compact means table (pvconv.py:68-90)
+__global__ void __launch_bounds__(256)
+vox_edge_large_kernel(const float* __restrict__ feat, const int* __restrict__ ws, const float* __restrict__ means,
+                      int C, int N, int ntiles, int ucap, float* __restrict__ edge)
+{
+    const int b = blockIdx.z, c = blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= N) return;
+    const VoxWs L = vox_ws_layout(N, ntiles);
+    const int sg = ws[(size_t)b * L.stride + L.off_segof + i];
+    const float f = feat[((size_t)b * C + c) * N + i];
+    float* E = edge + (size_t)b * 2 * C * N;
+    E[(size_t)c * N + i] = sg >= 0 ? __fsub_rn(f, means[((size_t)b * C + c) * ucap + sg]) : 0.f;
+    E[((size_t)C + c) * N + i] = f;
+}
+
+struct VoxLarge { size_t keys_in, keys_out, vals_in, vals_out, cub, cub_bytes, total; int bits; };
+
+// layout of the extra workspace of the scan-sized path, placed after the tables / means / counters of vox_ws_need
+static bool vox_large_layout(int B, int N, long long s, size_t base, VoxLarge& V)
+{
+    const long long nkeys = (long long)B * (s + 1);
+    if (nkeys > 0xffffffffLL || (long long)B * N > 0x7fffffffLL) return false;
+    int bits = 1;
+    while (bits < 32 && (1ll << bits) < nkeys) ++bits;
+    V.bits = bits;
+    const size_t n = (size_t)B * N;
+    size_t cb = 0;
+    if (cub::DeviceRadixSort::SortPairs(nullptr, cb, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr,
+                                        (int*)nullptr, (int)n, 0, bits) != cudaSuccess) return false;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t o = al(base);
+    V.keys_in = o; o += al(n * 4);
+    V.keys_out = o; o += al(n * 4);
+    V.vals_in = o; o += al(n * 4);
+    V.vals_out = o; o += al(n * 4);
+    V.cub = o; V.cub_bytes = cb; o += al(cb);
+    V.total = o;
+    return true;
+}
+
 template <bool SPH>
 int voxelize_impl(const float* feat, const void* coords, int B, int C, int N, int r,
                   float* out, int* ind, int* cnt, float* edge, void* workspace, size_t ws_bytes, cudaStream_t st)
@@ -810,6 +991,40 @@ int voxelize_impl(const float* feat, const void* coords, int B, int C, int N, in
         const int rc2 = vox_means_launch(feat, B, C, N, 0, B, plan, edge, ws, st);
         if (rc2 != RI_OK) return rc2;
         return vox_fill_launch(B, C, N, s, 0, B, plan, out, cnt, ws, st);
+    }
+    // scan-sized clouds: global sort + the same means / grid-writer phases (deterministic); needs the larger workspace
+    if (N > kSmallCloudMax && (s_ll % 4 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)cnt % 16 == 0) && B <= 65535 &&
+        C <= 65535 && workspace != nullptr && getenv("RI_VOX_ATOMIC") == nullptr) {
+        VoxLarge V;
+        const size_t base = vox_ws_need(plan, B, C, N);
+        if (vox_large_layout(B, N, s_ll, base, V) && ws_bytes >= V.total) {
+            unsigned char* wb = reinterpret_cast<unsigned char*>(workspace);
+            int* ws = reinterpret_cast<int*>(workspace);
+            unsigned* keys_in = reinterpret_cast<unsigned*>(wb + V.keys_in);
+            unsigned* keys_out = reinterpret_cast<unsigned*>(wb + V.keys_out);
+            int* vals_in = reinterpret_cast<int*>(wb + V.vals_in);
+            int* vals_out = reinterpret_cast<int*>(wb + V.vals_out);
+            vox_keys_large_kernel<SPH><<<dim3((N + 255) / 256, B), 256, 0, st>>>(coords, N, r, s, ind, keys_in, vals_in);
+            RI_LAUNCH_CHECK();
+            size_t cb = V.cub_bytes;
+            cudaError_t ec = cub::DeviceRadixSort::SortPairs(wb + V.cub, cb, keys_in, keys_out, vals_in, vals_out,
+                                                             (int)((size_t)B * N), 0, V.bits, st);
+            if (ec != cudaSuccess) return (int)ec;
+            vox_table_large_kernel<<<B, kLgThreads, 0, st>>>(keys_out, vals_out, N, s, plan.tile_cells, plan.ntiles, ws);
+            RI_LAUNCH_CHECK();
+            float* means = reinterpret_cast<float*>(ws + (size_t)B * plan.L.stride);
+            const int ucap = (N + 3) / 4 * 4;
+            if (C > 0) {
+                vox_means_large_kernel<<<dim3((N + 255) / 256, (C + kLgChans - 1) / kLgChans, B), 256, 0, st>>>(
+                    feat, ws, C, N, plan.ntiles, ucap, means);
+                RI_LAUNCH_CHECK();
+                if (edge != nullptr) {
+                    vox_edge_large_kernel<<<dim3((N + 255) / 256, C, B), 256, 0, st>>>(feat, ws, means, C, N, plan.ntiles, ucap, edge);
+                    RI_LAUNCH_CHECK();
+                }
+            }
+            return vox_fill_launch(B, C, N, s, 0, B, plan, out, cnt, ws, st);
+        }
     }
     // fallback: memset + atomics (also covers N == 0)
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)B * C * s * sizeof(float), st);
@@ -839,9 +1054,14 @@ extern "C" size_t ri_voxelize_workspace_bytes(int B, int C, int N, int r)
     const long long s = (long long)r * r * r;
     const int tile_cells = (int)(s < kTileCells ? s : kTileCells);
     const int ntiles = (int)((s + tile_cells - 1) / tile_cells);
-    return (size_t)B * vox_ws_layout(N, ntiles).stride * sizeof(int) +            // per-cloud tables
-           (size_t)B * C * ((N + 3) / 4 * 4) * sizeof(float) +                   // compact cell means [B][C][<=N]
-           kMaxFillCalls * sizeof(int) + 16;                                      // work counters
+    size_t need = (size_t)B * vox_ws_layout(N, ntiles).stride * sizeof(int) +     // per-cloud tables
+                  (size_t)B * C * ((N + 3) / 4 * 4) * sizeof(float) +            // compact cell means [B][C][<=N]
+                  kMaxFillCalls * sizeof(int) + 16;                               // work counters
+    if (N > kSmallCloudMax) {                                                     // scan-sized clouds: sort buffers
+        VoxLarge V;
+        if (vox_large_layout(B, N, s, need, V)) need = V.total + 16;
+    }
+    return need;
 }
 
 extern "C" int ri_sph_voxelize_f32(const float* feat, const float* coords, int B, int C, int N, int r,
