@@ -164,7 +164,7 @@ template <int P>
 __global__ void __launch_bounds__(kSdThreads + 32, 1)
 devox_stream_kernel(const float* __restrict__ coords, const float* __restrict__ feat, int B, int C, int N, int r,
                     int TS, int nt, uint32_t slot_bytes, int R,
-                    float* __restrict__ outs, int* __restrict__ inds, float* __restrict__ wgts)
+                    float* __restrict__ outs, int* __restrict__ inds, float* __restrict__ wgts, int dbg_skip)
 {
     extern __shared__ __align__(128) unsigned char sd_smem[];
     __shared__ __align__(8) uint64_t full[kSdMaxRing];
@@ -261,6 +261,7 @@ devox_stream_kernel(const float* __restrict__ coords, const float* __restrict__ 
             const int tile_base = t * TS * r2;
 #pragma unroll
             for (int p = 0; p < P; ++p) {
+                if (dbg_skip) break;
                 const int base = (id0[p] & 0x0fffffff) - tile_base;
                 const int hc = (id0[p] >> 28) & 1, hb = ((id0[p] >> 29) & 1) * r, ha = ((id0[p] >> 30) & 1) * r2;
                 if ((tl[p] & 0xff) == t) {
@@ -346,7 +347,8 @@ static int sd_launch(const SdPlan& pl, const float* coords, const float* feat, i
     ri_prefer_step_carveout(kern);
     const long long planes = (long long)B * C;
     const int grid = planes < ri_num_sms() ? (int)planes : ri_num_sms();
-    kern<<<grid, kSdThreads + 32, smem, st>>>(coords, feat, B, C, N, r, pl.TS, pl.nt, pl.slot_bytes, pl.R, outs, inds, wgts);
+    kern<<<grid, kSdThreads + 32, smem, st>>>(coords, feat, B, C, N, r, pl.TS, pl.nt, pl.slot_bytes, pl.R, outs, inds, wgts,
+                                              getenv("RI_DEVOX_DBG_SKIP") != nullptr ? 1 : 0);
     RI_LAUNCH_CHECK();
     return RI_OK;
 }
