@@ -289,7 +289,7 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
 
 template <bool SPH>
 __global__ void __launch_bounds__(kFrontThreads)
-vox_front_kernel(const float* __restrict__ points, int pstride, const float* __restrict__ mean,
+vox_front_kernel(const float* __restrict__ points, int pstride, float* __restrict__ mean, int own_mean, float mean_factor,
                  const float* __restrict__ feat, int C, int N, int P, int r, int s, int tile_cells, int ntiles,
                  int shape, float eps, int norm_mode, int ucap,
                  float* __restrict__ norm_coords, int* __restrict__ vox_coords, int* __restrict__ ind,
@@ -327,7 +327,31 @@ vox_front_kernel(const float* __restrict__ points, int pstride, const float* __r
 
     // ---- coordinate prologue (prologue.cu::prologue_kernel, same arithmetic)
     const float* Pt = points + (size_t)b * pstride * N;
-    const float mx = mean[b * 3 + 0], my = mean[b * 3 + 1], mz = mean[b * 3 + 2];
+    __shared__ float smean3[3];
+    if (own_mean) {
+        // The per-cloud mean in the order torch's reduce kernel uses for a contiguous row of 128 <= N < 8192 floats, N % 4 == 0
+        // (ATen/native/cuda/Reduce.cuh: one warp per output, vectorize_input with four accumulators per lane over float4
+        // loads strided by 32 lanes, ((v0 + v1) + v2) + v3, shuffle-down tree with offsets 16, 8, 4, 2, 1, times factor):
+        // the same bits as coords.mean(2) — the engine verifies that once against torch before it relies on it.
+        if (tid < 96) {
+            const int a = tid >> 5, l = tid & 31;
+            const float4* row = reinterpret_cast<const float4*>(Pt + (size_t)a * N);
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+            for (int idx = l; idx * 4 + 3 < N; idx += 32) {
+                const float4 x = row[idx];
+                v0 = __fadd_rn(v0, x.x); v1 = __fadd_rn(v1, x.y); v2 = __fadd_rn(v2, x.z); v3 = __fadd_rn(v3, x.w);
+            }
+            float v = __fadd_rn(__fadd_rn(__fadd_rn(v0, v1), v2), v3);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, o));
+            if (l == 0) { smean3[a] = __fmul_rn(v, mean_factor); if (publish) mean[b * 3 + a] = smean3[a]; }
+        }
+        __syncthreads();
+    } else if (tid < 3) {
+        smean3[tid] = mean[b * 3 + tid];
+    }
+    if (!own_mean) __syncthreads();
+    const float mx = smean3[0], my = smean3[1], mz = smean3[2];
     const size_t o3 = (size_t)b * 3 * N;
     float denom = 1.0f;
     if (shape != 0) {
@@ -1204,7 +1228,13 @@ extern "C" int ri_vox_front_f32(const float* points, int pstride, const float* m
     if (e != cudaSuccess) return (int)e;
     ri_prefer_step_carveout(kern);
     dim3 grid(C > 0 ? (C + kMeanChans - 1) / kMeanChans : 1, B);
-    kern<<<grid, kFrontThreads, smem, (cudaStream_t)stream>>>(points, pstride, mean, feat, C, N, plan.P, r, (int)s_ll,
+    // norm_mode bit 8: compute the per-cloud mean inside the kernel (torch's reduction order) and write it to `mean`
+    const int own_mean = (norm_mode & 0x100) != 0;
+    norm_mode &= 0xff;
+    if (own_mean && (N < 128 || (N & 3) != 0 || ((uintptr_t)points & 15) != 0)) return RI_ERR_UNSUPPORTED;
+    const float mean_factor = (float)(3LL * B) / (float)(3LL * B * N);           // mean_kernel_cuda: num_outputs / numel
+    kern<<<grid, kFrontThreads, smem, (cudaStream_t)stream>>>(points, pstride, const_cast<float*>(mean), own_mean, mean_factor,
+                                                              feat, C, N, plan.P, r, (int)s_ll,
                                                               plan.tile_cells, plan.ntiles, shape, eps, norm_mode, ucap,
                                                               norm_coords, vox_coords, ind, ws, means, edge);
     RI_LAUNCH_CHECK();

@@ -37,7 +37,7 @@ class FrontEnd:
 
     def __init__(self, B, N, C, k=20, r=32, voxel_shape='spherical', normalize=False, eps=0.0,
                  device='cuda', use_graph=True, overlap=True, grid_chunks=None, devox_side_stream=True,
-                 knn_after_front=True, join_before_devox=None):
+                 knn_after_front=True, join_before_devox=None, fuse_mean=True):
         if voxel_shape not in ('spherical', 'cube'):
             raise ValueError('voxel_shape must be "spherical" or "cube"')
         self.B, self.N, self.C, self.k, self.r = int(B), int(N), int(C), int(k), int(r)
@@ -107,6 +107,13 @@ class FrontEnd:
             self.h_edge = torch.empty((B, 2 * C, N), dtype=f32).pin_memory()
         self._graph = None
         self._fused_front = self.grid_chunks == 1 and N <= 1024 and s % 4 == 0
+        # in-kernel mean (torch's reduction order, csrc/voxelize.cu): candidate only where that order is the one analysed
+        # (128 <= N, N % 4 == 0); switched on by _verify_own_mean() at the first forward(), never silently
+        self._own_mean = False
+        # 3 B >= 16 outputs: below that torch widens its blocks (more lanes per output, another summation tree)
+        self._own_mean_checked = not (fuse_mean and self._fused_front and N >= 128 and N % 4 == 0 and 3 * B >= 16)
+        with torch.cuda.device(dev):
+            self._mean_buf = torch.zeros((B, 3), dtype=f32, device=dev)
 
     # bytes moved per host-facing call
     @property
@@ -138,16 +145,18 @@ class FrontEnd:
     def _branch_b(self, join=None, fork=None):
         st = torch.cuda.current_stream().cuda_stream
         B, N, C, r = self.B, self.N, self.C, self.r
-        # Coordinate prologue.  The per-cloud mean stays torch's own reduction (its summation order defines the bits
-        # the binning must see); everything after it is bit-identical to the module shells (modules/voxelization.py) —
-        # asserted by tests/test_parity_gpu.py.
-        mean = self.points[:, :3, :].mean(2)
+        # Coordinate prologue: bit-identical to the module shells (modules/voxelization.py) — asserted by tests/test_parity_gpu.py.
         sph = self.voxel_shape == 'spherical'
         shape = 2 if sph else (1 if self.normalize else 0)
-        if self.grid_chunks == 1 and N <= 1024 and (r ** 3) % 4 == 0:
+        fused = self.grid_chunks == 1 and N <= 1024 and (r ** 3) % 4 == 0
+        own_mean = fused and self._own_mean
+        # The per-cloud mean: torch's own reduction (its summation order defines the bits the binning must see), or — on the
+        # fused path, once _verify_own_mean() has seen it reproduce torch's bits for this shape — the same order inside the kernel
+        mean = self._mean_buf if own_mean else self.points[:, :3, :].mean(2)
+        if fused:
             # prologue + prepare + means/edge in one launch, then the grid writer
             _check(_L.ri_vox_front_f32(self.points.data_ptr(), 6, mean.data_ptr(), self.features.data_ptr(), B, C, N, r,
-                                       shape, float(self.eps), self.NORM_MODE, self.norm_coords.data_ptr(),
+                                       shape, float(self.eps), self.NORM_MODE | (0x100 if own_mean else 0), self.norm_coords.data_ptr(),
                                        self._vox_coords.data_ptr(), self.ind.data_ptr(), self.edge.data_ptr(),
                                        self._ws.data_ptr(), self._ws_bytes, st), 'ri_vox_front')
             if fork is not None:
@@ -246,7 +255,33 @@ class FrontEnd:
             self._branch_a()
             self._branch_b()
 
+    def _verify_own_mean(self):
+        """Run the fused prefix once with the in-kernel mean on a seeded random probe batch of this engine's shape and compare
+        the means it wrote with torch's `probe[:, :3].mean(2)` bit for bit; only then is the torch reduction dropped from the
+        step (a torch build with another reduction heuristic simply keeps the torch kernel)."""
+        self._own_mean_checked = True
+        B, N, C, r = self.B, self.N, self.C, self.r
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            shape = 2 if self.voxel_shape == 'spherical' else (1 if self.normalize else 0)
+            g = torch.Generator(device=self.device); g.manual_seed(20261018)
+            ok = True
+            for stride in (7, 3, 11):                      # three probes: 9 B sums have to come out bit-identical
+                probe = torch.randn((B, 6, N), dtype=torch.float32, device=self.device, generator=g) * 3.0 + 0.7
+                probe[:, :3, ::stride] *= 1e3              # mixed magnitudes: any other summation order changes low bits
+                rc = _L.ri_vox_front_f32(probe.data_ptr(), 6, self._mean_buf.data_ptr(), self.features.data_ptr(), B, C, N, r,
+                                         shape, float(self.eps), self.NORM_MODE | 0x100, self.norm_coords.data_ptr(),
+                                         self._vox_coords.data_ptr(), self.ind.data_ptr(), self.edge.data_ptr(),
+                                         self._ws.data_ptr(), self._ws_bytes, st)
+                if rc != 0:
+                    return
+                want = probe[:, :3, :].mean(2)
+                ok = ok and bool(torch.equal(want, self._mean_buf)) and bool(torch.isfinite(want).all())
+            self._own_mean = ok
+
     def _capture(self):
+        if not self._own_mean_checked:
+            self._verify_own_mean()
         with torch.cuda.device(self.device):
             warm = torch.cuda.Stream(device=self.device)
             warm.wait_stream(torch.cuda.current_stream())
@@ -264,6 +299,8 @@ class FrontEnd:
         """One step on the device-resident `points` / `features` buffers (asynchronous)."""
         with torch.cuda.device(self.device):
             if not self.use_graph:
+                if not self._own_mean_checked:
+                    self._verify_own_mean()
                 self._step()
                 return
             if self._graph is None:
@@ -312,7 +349,7 @@ class FrontEndLanes:
     ALU-bound k-NN run under the HBM-bound grid write / devoxelize of step i.  An engine is never replayed before its own
     previous step has finished (per-engine event).
 
-        lanes = FrontEndLanes(engines, lanes=2)
+        lanes = FrontEndLanes(engines, lanes=2)     # engines built with fuse_mean=False: best throughput in flight
         lanes.begin()                 # the launch streams pick up after the current stream
         for i in range(K): lanes.forward(i)
         lanes.end()                   # the current stream waits for every step in flight

@@ -571,3 +571,25 @@ def test_knn_ties_and_short_reference_sets_vs_oracle(ri, oracle, k, n, m):
     od1, od2, oi1, oi2 = oracle.knn(A(x1), A(x2), k)
     assert np.array_equal(A(i1), oi1) and np.array_equal(A(i2), oi2)
     assert np.array_equal(A(d1), od1) and np.array_equal(A(d2), od2)
+
+
+@pytest.mark.parametrize("B,N", [(32, 1024), (6, 1000), (8, 128), (16, 512), (1, 1024), (5, 512)])
+def test_in_kernel_mean_reproduces_torch(ri, B, N):
+    """The fused prefix kernel's own per-cloud mean (torch's reduction order restated, csrc/voxelize.cu) equals
+    `coords.mean(2)` bit for bit on awkward data, and the engine only drops the torch kernel after checking that itself."""
+    fe = ri.FrontEnd(B, N, 5, k=8, r=16, voxel_shape="cube")
+    g = torch.Generator(device="cuda"); g.manual_seed(N)
+    pts = torch.randn((B, 6, N), device="cuda", generator=g) * 5 - 1.3
+    pts[:, :3, ::5] *= 300.0
+    fe.load(pts, torch.randn((B, 5, N), device="cuda", generator=g))
+    fe.forward(); torch.cuda.synchronize()
+    assert fe._own_mean_checked
+    if 3 * B >= 16:
+        assert fe._own_mean, "the engine did not accept the in-kernel mean for this shape"
+        assert torch.equal(fe._mean_buf, pts[:, :3, :].mean(2))
+    else:
+        assert not fe._own_mean                            # few outputs: torch reduces with wider blocks, the engine keeps torch's kernel
+    # and the step built on it still equals the module path (torch mean) bit for bit
+    vox = ri.modules.Voxelization(16, normalize=False)
+    avg, ind, nc = vox(fe.features, pts[:, :3].contiguous())
+    assert torch.equal(ind, fe.ind) and torch.equal(nc, fe.norm_coords) and torch.equal(avg.reshape(B, 5, -1), fe.grid.reshape(B, 5, -1))

@@ -11,7 +11,7 @@ NE = 6
 fes = []
 for q in range(NE):
     fe = ri_b200.FrontEnd(B, N, C, k=k, r=r, voxel_shape=shape, join_before_devox={"0": False, "1": True}.get(os.environ.get("JOIN", ""), None),
-                          knn_after_front=os.environ.get("KNN_AFTER", "1") == "1", overlap=os.environ.get("OVERLAP", "1") == "1")
+                          knn_after_front=os.environ.get("KNN_AFTER", "1") == "1", fuse_mean=os.environ.get("FUSE_MEAN", "1") == "1", overlap=os.environ.get("OVERLAP", "1") == "1")
     fe.load(synth.make_clouds(B, N, seed=q), synth.make_features(B, C, N, seed=q)); fes.append(fe)
 torch.cuda.synchronize()
 for ne in (int(os.environ.get("NE", 3)),):
