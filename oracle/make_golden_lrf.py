@@ -19,35 +19,37 @@ sys.path.insert(0, ROOT)
 
 
 def change_coords_torch(coords):
-    b, _, n = coords.shape
-    norm_coords = coords - coords.mean(dim=2, keepdim=True)
-    rank = torch.argsort(norm_coords.norm(dim=1), dim=1, descending=True)
-    batch_base_x = torch.zeros(b, 3, 1).to(norm_coords)
-    batch_base_y = torch.zeros(b, 3, 1).to(norm_coords)
-    for i in range(b):
-        base_x = norm_coords[i, :, rank[i, 0]]
-        assert (base_x.norm() > 1e-5)
-        base_x = base_x / base_x.norm()
-        for j in range(1, n):
-            base_y = norm_coords[i, :, rank[i, j]]
-            if base_y.norm() < 1e-5:
+    """The torch calls of pvcnn_classify.py:153-184 in their order (mean, norm(dim=1), argsort(descending), per-vector norm(),
+    (a*b).sum(), bmm, cross, norm(dim=1)) — written out here, not imported: see the module docstring."""
+    nb, _, npts = coords.shape
+    centred = coords - coords.mean(dim=2, keepdim=True)                                   # :154
+    by_radius = torch.argsort(centred.norm(dim=1), dim=1, descending=True)                # :155
+    ex = torch.zeros(nb, 3, 1).to(centred)
+    ey = torch.zeros(nb, 3, 1).to(centred)
+    for c in range(nb):
+        first = centred[c, :, by_radius[c, 0]]                                            # :159
+        assert first.norm() > 1e-5                                                        # :160
+        first = first / first.norm()
+        second, cosang = None, None
+        for q in range(1, npts):                                                          # :162-169
+            cand = centred[c, :, by_radius[c, q]]
+            if cand.norm() < 1e-5:
                 continue
-            base_y = base_y / base_y.norm()
-            lamda = (base_x * base_y).sum()
-            if (lamda < 0.9 and lamda > -0.9):
+            cand = cand / cand.norm()
+            cosang = (first * cand).sum()
+            if cosang < 0.9 and cosang > -0.9:
+                second = cand
                 break
-        assert (lamda < 0.9 and lamda > -0.9)
-        batch_base_x[i, :, :] = base_x.unsqueeze(1)
-        batch_base_y[i, :, :] = base_y.unsqueeze(1)
-    batch_base_x -= batch_base_y * (batch_base_x.permute(0, 2, 1).bmm(batch_base_y))
-    assert (batch_base_x.norm(dim=1, keepdim=True) < 1e-5).sum() < 1
-    batch_base_x /= batch_base_x.norm(dim=1, keepdim=True)
-    batch_base_z = batch_base_x.cross(batch_base_y, dim=1)
-    batch_base_z = batch_base_z / batch_base_z.norm(dim=1, keepdim=True)
-    new_x = batch_base_x.permute(0, 2, 1).bmm(norm_coords)
-    new_y = batch_base_y.permute(0, 2, 1).bmm(norm_coords)
-    new_z = batch_base_z.permute(0, 2, 1).bmm(norm_coords)
-    return torch.cat((new_x, new_y, new_z), dim=1), torch.cat((batch_base_x, batch_base_y, batch_base_z), dim=2).permute(0, 2, 1)
+        assert second is not None                                                         # :170
+        ex[c, :, :] = first.unsqueeze(1)
+        ey[c, :, :] = second.unsqueeze(1)
+    ex -= ey * (ex.permute(0, 2, 1).bmm(ey))                                              # :175 Gram-Schmidt, y kept
+    assert (ex.norm(dim=1, keepdim=True) < 1e-5).sum() < 1                                # :176
+    ex /= ex.norm(dim=1, keepdim=True)                                                    # :177
+    ez = ex.cross(ey, dim=1)                                                              # :179
+    ez = ez / ez.norm(dim=1, keepdim=True)                                                # :180
+    rows = [axis.permute(0, 2, 1).bmm(centred) for axis in (ex, ey, ez)]                  # :181-183
+    return torch.cat(rows, dim=1), torch.cat((ex, ey, ez), dim=2).permute(0, 2, 1)
 
 
 def main():

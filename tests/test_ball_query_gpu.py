@@ -81,24 +81,19 @@ def test_ball_query_errors(ri):
         torch.ops.ri.grouping(x, torch.zeros(1, 4, 4, device="cuda", dtype=torch.int64))
 
 
-def _torch_local_ppf(inputs, grouper, neighbor_num):
-    """The reference's own torch operations (pvcnn_classify.py:252-269), run on the GPU through the BallQuery module mirror."""
-    coords = inputs[:, :3, :]
-    normals = inputs[:, 3:6, :]
-    center_coords = coords
-    center_normals = normals
-    neighbor_coords_normals = grouper(coords, center_coords, normals)
-    neighbor_coords = neighbor_coords_normals[:, :3, :, :]
-    neighbor_normals = neighbor_coords_normals[:, 3:, :, :]
-    center_coords_k_repeat = center_coords.unsqueeze(2).expand(-1, -1, neighbor_num, -1)
-    center_normals_k_repeat = center_normals.unsqueeze(2).expand(-1, -1, neighbor_num, -1)
-    d = center_coords_k_repeat - neighbor_coords
-    d_norm = torch.norm(d, dim=1, p=2, keepdim=True)
-    d_unit = d / d_norm
-    nr_d = torch.acos(neighbor_normals.mul(d_unit).sum(dim=1, keepdim=True).clamp(-1, 1))
-    ni_d = torch.acos(center_normals_k_repeat.mul(d_unit).sum(dim=1, keepdim=True).clamp(-1, 1))
-    nr_ni = torch.acos(neighbor_normals.mul(center_normals_k_repeat).sum(dim=1, keepdim=True).clamp(-1, 1))
-    return torch.cat((nr_d, ni_d, nr_ni, d_norm), dim=1)
+def _torch_local_ppf(cloud, grouper, u):
+    """The torch calls of pvcnn_classify.py:252-269 in their order, through the BallQuery module mirror: grouped (relative)
+    coordinates and normals [b,6,u,m]; d = centre - grouped; norm(dim=1); d / norm; three acos(clamp(sum(mul)))."""
+    xyz, nrm = cloud[:, :3, :], cloud[:, 3:6, :]
+    grouped = grouper(xyz, xyz, nrm)                                         # [b, 6, u, m]
+    g_xyz, g_nrm = grouped[:, :3], grouped[:, 3:]
+    c_xyz = xyz.unsqueeze(2).expand(-1, -1, u, -1)
+    c_nrm = nrm.unsqueeze(2).expand(-1, -1, u, -1)
+    d = c_xyz - g_xyz
+    length = torch.norm(d, dim=1, p=2, keepdim=True)
+    unit = d / length
+    ang = lambda p, q: torch.acos(p.mul(q).sum(dim=1, keepdim=True).clamp(-1, 1))
+    return torch.cat((ang(g_nrm, unit), ang(c_nrm, unit), ang(g_nrm, c_nrm), length), dim=1)
 
 
 @pytest.mark.parametrize("B,N,U,radius", [(32, 1024, 128, 0.3), (3, 500, 16, 0.25), (2, 1000, 7, 0.5)])

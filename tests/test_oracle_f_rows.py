@@ -12,20 +12,17 @@ def test_local_ppf_oracle_equals_reference_torch_ops_on_cpu(oracle):
     nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
     idx = oracle.ball_query(xyz, xyz, 0.4, U)                                   # [B,M,U]
     got = oracle.local_ppf(xyz, nrm, idx)
-    # the reference's ops: BallQuery.forward (ball_query.py:16-35) then pvcnn_classify.py:258-269, torch on the CPU
-    coords, normals = torch.from_numpy(xyz), torch.from_numpy(nrm)
+    # the reference's torch calls in their order (BallQuery.forward, ball_query.py:16-35, then pvcnn_classify.py:258-269), CPU
+    xyz_t, nrm_t = torch.from_numpy(xyz), torch.from_numpy(nrm)
     gi = torch.from_numpy(idx.astype(np.int64)).reshape(B, 1, N * U).expand(-1, 3, -1)
-    nb_c = torch.gather(coords, 2, gi).reshape(B, 3, N, U) - coords.unsqueeze(-1)        # grouping - centres
-    nb_n = torch.gather(normals, 2, gi).reshape(B, 3, N, U)
-    g = torch.cat([nb_c, nb_n], 1).permute(0, 1, 3, 2)                                    # [b, 6, u, m]
-    neighbor_coords, neighbor_normals = g[:, :3], g[:, 3:]
-    ck = coords.unsqueeze(2).expand(-1, -1, U, -1); nk = normals.unsqueeze(2).expand(-1, -1, U, -1)
-    d = ck - neighbor_coords
-    d_norm = torch.norm(d, dim=1, p=2, keepdim=True)
-    d_unit = d / d_norm
-    want = torch.cat((torch.acos(neighbor_normals.mul(d_unit).sum(dim=1, keepdim=True).clamp(-1, 1)),
-                      torch.acos(nk.mul(d_unit).sum(dim=1, keepdim=True).clamp(-1, 1)),
-                      torch.acos(neighbor_normals.mul(nk).sum(dim=1, keepdim=True).clamp(-1, 1)), d_norm), dim=1).numpy()
+    g_xyz = (torch.gather(xyz_t, 2, gi).reshape(B, 3, N, U) - xyz_t.unsqueeze(-1)).permute(0, 1, 3, 2)     # relative, [b,3,u,m]
+    g_nrm = torch.gather(nrm_t, 2, gi).reshape(B, 3, N, U).permute(0, 1, 3, 2)
+    c_xyz = xyz_t.unsqueeze(2).expand(-1, -1, U, -1); c_nrm = nrm_t.unsqueeze(2).expand(-1, -1, U, -1)
+    d = c_xyz - g_xyz
+    length = torch.norm(d, dim=1, p=2, keepdim=True)
+    unit = d / length
+    ang = lambda p, q: torch.acos(p.mul(q).sum(dim=1, keepdim=True).clamp(-1, 1))
+    want = torch.cat((ang(g_nrm, unit), ang(c_nrm, unit), ang(g_nrm, c_nrm), length), dim=1).numpy()
     assert got.shape == want.shape == (B, 4, U, N)
     assert np.abs(got[:, 3] - want[:, 3]).max() <= 1e-6
     edge = np.abs(np.cos(want[:, :3])) > 1 - 1e-4
