@@ -1,6 +1,11 @@
-"""BallQuery — same contract as /root/reference/PVCNN/modules/ball_query.py:9-40."""
+"""BallQuery — neighbourhood grouping module with the reference's contract (PVCNN/modules/ball_query.py:10-35 of the reference):
+constructor `(radius, num_neighbors, include_coordinates=True)`, `forward(points_coords, centers_coords, points_features=None)`
+returning the grouped tensor laid out `[B, C', U, M]` (neighbours before centres), where C' is 3 relative coordinates and / or the
+grouped feature channels.  Everything heavy runs in csrc/ballquery.cu (`ri_ball_query_f32`, `ri_grouping_f32`).
+
+For the models' local PPF branch prefer `functional.ball_local_ppf`, which never materialises the grouped tensors."""
 import torch
-import torch.nn as nn
+from torch import nn
 
 from .. import functional as F
 
@@ -10,25 +15,25 @@ __all__ = ['BallQuery']
 class BallQuery(nn.Module):
     def __init__(self, radius, num_neighbors, include_coordinates=True):
         super().__init__()
-        self.radius = radius
-        self.num_neighbors = num_neighbors
-        self.include_coordinates = include_coordinates
+        self.radius, self.num_neighbors, self.include_coordinates = radius, num_neighbors, include_coordinates
+
+    def neighbours(self, points_coords, centers_coords):
+        """int32 [B, M, U]: the first `num_neighbors` points inside the ball of each centre, in index order (self excluded)."""
+        return F.ball_query(centers_coords.contiguous(), points_coords.contiguous(), self.radius, self.num_neighbors)
 
     def forward(self, points_coords, centers_coords, points_features=None):
-        points_coords = points_coords.contiguous()
-        centers_coords = centers_coords.contiguous()
-        neighbor_indices = F.ball_query(centers_coords, points_coords, self.radius, self.num_neighbors)     # [b, m, u]
-        neighbor_coordinates = F.grouping(points_coords, neighbor_indices)                                  # [b, 3, m, u]
-        neighbor_coordinates = neighbor_coordinates - centers_coords.unsqueeze(-1)
-        if points_features is None:
-            assert self.include_coordinates, 'No Features For Grouping'
-            neighbor_features = neighbor_coordinates
-        else:
-            neighbor_features = F.grouping(points_features, neighbor_indices)                               # [b, c, m, u]
-            if self.include_coordinates:
-                neighbor_features = torch.cat([neighbor_coordinates, neighbor_features], dim=1)
-        return neighbor_features.permute(0, 1, 3, 2)                                                        # [b, c, u, m]
+        if points_features is None and not self.include_coordinates:
+            raise AssertionError('No Features For Grouping')
+        idx = self.neighbours(points_coords, centers_coords)
+        channels = []
+        if self.include_coordinates or points_features is None:
+            # coordinates of the neighbours relative to their centre, [B, 3, M, U]
+            channels.append(F.grouping(points_coords.contiguous(), idx) - centers_coords.contiguous()[..., None])
+        if points_features is not None:
+            channels.append(F.grouping(points_features, idx))                 # [B, C, M, U]
+        grouped = channels[0] if len(channels) == 1 else torch.cat(channels, dim=1)
+        return grouped.transpose(2, 3)                                        # [B, C', U, M]
 
     def extra_repr(self):
-        return 'radius={}, num_neighbors={}{}'.format(
-            self.radius, self.num_neighbors, ', include coordinates' if self.include_coordinates else '')
+        tail = ', include coordinates' if self.include_coordinates else ''
+        return f'radius={self.radius}, num_neighbors={self.num_neighbors}{tail}'
