@@ -18,6 +18,9 @@
 #include "ri_common.cuh"
 #include "ppf_math.cuh"
 
+int ri_launch_knn_warp(const float* queries, const float* refs, int B, int n, int m, int k, float* dist, int* idx,
+                       cudaStream_t st);
+
 namespace {
 
 constexpr float kUndefDist = 10000.0f;   // knn/knn.cuh:3 (UNDEFINE_VALUE)
@@ -219,9 +222,11 @@ knn_generic_kernel(const float* __restrict__ queries, const float* __restrict__ 
 }
 
 int launch_knn(const float* queries, const float* refs, int B, int c, int n, int m, int k,
-               float* dist, int* idx, cudaStream_t st)
+               float* dist, int* idx, cudaStream_t st, bool thread_per_query)
 {
     if (B == 0 || n == 0) return RI_OK;
+    if (!thread_per_query && c == 3 && k <= 32 && m >= 1 && m <= 1024)
+        return ri_launch_knn_warp(queries, refs, B, n, m, k, dist, idx, st);      // knn_warp.cu: a warp per query
     dim3 grid((n + kQueriesPerCta - 1) / kQueriesPerCta, B);
     const size_t smem = (size_t)(m < kRefTile ? (m > 0 ? m : 1) : kRefTile) * sizeof(float4);
     static bool carveout_set = false;
@@ -250,7 +255,17 @@ extern "C" int ri_knn_f32(const float* xyz1, const float* xyz2, int B, int c, in
 {
     if (B < 0 || c <= 0 || n < 0 || m < 0 || k <= 0) return RI_ERR_BAD_ARG;
     if (B > 65535) return RI_ERR_UNSUPPORTED;
-    return launch_knn(xyz1, xyz2, B, c, n, m, k, dist1, idx1, (cudaStream_t)stream);
+    return launch_knn(xyz1, xyz2, B, c, n, m, k, dist1, idx1, (cudaStream_t)stream, false);
+}
+
+// The thread-per-query form for every shape (what ri_knn_f32 runs for m > 1024, c != 3 or k > 32): kept addressable so the
+// tests can hold the two forms against each other.
+extern "C" int ri_knn_thread_f32(const float* xyz1, const float* xyz2, int B, int c, int n, int m, int k,
+                                 float* dist1, int* idx1, void* stream)
+{
+    if (B < 0 || c <= 0 || n < 0 || m < 0 || k <= 0) return RI_ERR_BAD_ARG;
+    if (B > 65535) return RI_ERR_UNSUPPORTED;
+    return launch_knn(xyz1, xyz2, B, c, n, m, k, dist1, idx1, (cudaStream_t)stream, true);
 }
 
 extern "C" int ri_knn_bilateral_f32(const float* xyz1, const float* xyz2, int B, int c, int n, int m, int k,

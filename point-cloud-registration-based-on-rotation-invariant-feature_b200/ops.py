@@ -49,6 +49,15 @@ def _workspace(device, nbytes):
 
 
 # ---------------------------------------------------------------------------------------------- KNN
+def _check_knn_shapes(xyz1, xyz2, k):
+    if xyz1.dim() != 3 or xyz2.dim() != 3:
+        raise RuntimeError("xyz1 / xyz2 must be [B, c, n] / [B, c, m] tensors")
+    if xyz1.shape[0] != xyz2.shape[0] or xyz1.shape[1] != xyz2.shape[1]:
+        raise RuntimeError("xyz1 and xyz2 must agree in batch size and channel count")
+    if k <= 0:
+        raise RuntimeError("k must be positive")
+
+
 GRID_KNN_MIN_REFS = 4096     # at and above this many reference points (c == 3, k <= 32) the hash-grid search is used
 
 
@@ -67,6 +76,7 @@ def _knn_dir(q, r, B, c, n, m, k, d, i, dev):
 def knn(xyz1: torch.Tensor, xyz2: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
     _req(xyz1, "xyz1", torch.float32); _req(xyz2, "xyz2", torch.float32)
     dev = _same_device(xyz1, xyz2)
+    _check_knn_shapes(xyz1, xyz2, k)
     B, c, n = xyz1.shape
     m = xyz2.shape[2]
     with torch.cuda.device(dev):
@@ -96,6 +106,7 @@ def knn_one(xyz1: torch.Tensor, xyz2: torch.Tensor, k: int) -> tuple[torch.Tenso
     """One direction only (queries xyz1 against references xyz2)."""
     _req(xyz1, "xyz1", torch.float32); _req(xyz2, "xyz2", torch.float32)
     dev = _same_device(xyz1, xyz2)
+    _check_knn_shapes(xyz1, xyz2, k)
     B, c, n = xyz1.shape
     m = xyz2.shape[2]
     with torch.cuda.device(dev):
@@ -103,6 +114,28 @@ def knn_one(xyz1: torch.Tensor, xyz2: torch.Tensor, k: int) -> tuple[torch.Tenso
         i1 = torch.empty((B, k, n), dtype=torch.int32, device=dev)
         _knn_dir(xyz1, xyz2, B, c, n, m, k, d1, i1, dev)
     return d1, i1
+
+
+@torch.library.custom_op("ri::knn_brute", mutates_args=())
+def knn_brute(xyz1: torch.Tensor, xyz2: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """One direction through the one-thread-per-query kernel regardless of size (csrc/knn.cu) — what the warp-per-query
+    kernel (csrc/knn_warp.cu) must equal."""
+    _req(xyz1, "xyz1", torch.float32); _req(xyz2, "xyz2", torch.float32)
+    dev = _same_device(xyz1, xyz2)
+    B, c, n = xyz1.shape
+    m = xyz2.shape[2]
+    _check_knn_shapes(xyz1, xyz2, k)
+    with torch.cuda.device(dev):
+        d1 = torch.empty((B, k, n), dtype=torch.float32, device=dev)
+        i1 = torch.empty((B, k, n), dtype=torch.int32, device=dev)
+        _check(_L.ri_knn_thread_f32(xyz1.data_ptr(), xyz2.data_ptr(), B, c, n, m, k, d1.data_ptr(), i1.data_ptr(), _stream()), "ri_knn")
+    return d1, i1
+
+
+@knn_brute.register_fake
+def _(xyz1, xyz2, k):
+    B, c, n = xyz1.shape
+    return xyz1.new_empty((B, k, n)), xyz1.new_empty((B, k, n), dtype=torch.int32)
 
 
 @torch.library.custom_op("ri::knn_grid", mutates_args=())
