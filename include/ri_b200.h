@@ -54,18 +54,6 @@ int ri_knn_thread_f32(const float* xyz1, const float* xyz2, int B, int c, int n,
 int ri_knn_bilateral_f32(const float* xyz1, const float* xyz2, int B, int c, int n, int m, int k,
                          float* dist1, float* dist2, int* idx1, int* idx2, void* stream);
 
-/* The same two calls with a workspace (>= ri_knn_workspace_bytes(B, n, m) bytes, 16-byte aligned): for c == 3, k <= 32 and
- * n, m <= 2048 the search is spatially pruned — both point sets are put in Morton order once (one small launch), queries
- * are processed in that order and every warp scans only the blocks of references its queries can still improve on,
- * nearest first, the list kept sorted by the key (distance, reference index).  Exact: every output bit equals
- * ri_knn_f32's (csrc/knn_pruned.cu).  Other shapes take ri_knn_f32's path.  xyz1 == xyz2 (self query) sorts one set. */
-size_t ri_knn_workspace_bytes(int B, int n, int m);
-int ri_knn_ws_f32(const float* xyz1, const float* xyz2, int B, int c, int n, int m, int k,
-                  float* dist1, int* idx1, void* workspace, size_t workspace_bytes, void* stream);
-int ri_knn_bilateral_ws_f32(const float* xyz1, const float* xyz2, int B, int c, int n, int m, int k,
-                            float* dist1, float* dist2, int* idx1, int* idx2,
-                            void* workspace, size_t workspace_bytes, void* stream);
-
 /* The same search for scan-sized clouds (~50k points, c == 3): uniform hash grid + ring expansion instead of the full
  * scan, results bit-identical to ri_knn_f32 (same distance expression, candidates ordered by (distance, index)).
  * k <= 32.  workspace >= ri_knn_grid_workspace_bytes(B, n, m) bytes, 16-byte aligned. */

@@ -17,9 +17,6 @@ SIGNATURES = {
     "ri_knn_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ri_knn_thread_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ri_knn_bilateral_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
-    "ri_knn_workspace_bytes": (_Z, [_I, _I, _I]),
-    "ri_knn_ws_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
-    "ri_knn_bilateral_ws_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "ri_knn_grid_workspace_bytes": (_Z, [_I, _I, _I]),
     "ri_knn_grid_f32": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "ri_knn_backward_f32": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),

@@ -104,3 +104,28 @@ def test_warp_is_deterministic_across_runs():
     for _ in range(5):
         d, i = torch.ops.ri.knn_one(a, a, 20)
         assert torch.equal(i, i0) and torch.equal(d, d0)
+
+
+@pytest.mark.parametrize("n,k", [(1024, 20), (640, 32), (1000, 8)])
+def test_warp_clustered_index_classes_take_the_streaming_path(n, k):
+    """References whose index classes modulo 32 are tight spatial clusters: one lane of the warp-per-query kernel then owns
+    all the near candidates, its threshold (k-th smallest per-lane minimum) admits hundreds of survivors, and the kernel has to
+    stream them instead of compacting them into its key buffer.  Same bits as the thread-per-query kernel."""
+    rng = np.random.default_rng(n + k)
+    centres = rng.standard_normal((32, 3)).astype(np.float32) * 2.0
+    x = np.empty((3, 3, n), np.float32)
+    for b in range(3):
+        cls = np.arange(n) % 32
+        x[b] = (centres[cls] + rng.standard_normal((n, 3)).astype(np.float32) * (1e-3 if b < 2 else 0.0)).T   # cloud 2: exact duplicates
+    assert_same(T(x), T(x), k)
+    q = T(rng.standard_normal((3, 3, 333)).astype(np.float32))
+    assert_same(q, T(x), k)
+
+
+def test_warp_runs_cross_cloud_boundaries():
+    # many small clouds: every warp's run of consecutive (cloud, query) pairs spans several clouds, odd sizes break the pairs
+    g = torch.Generator(device="cuda"); g.manual_seed(9)
+    for B, n, m in ((257, 7, 50), (64, 33, 33), (100, 1, 40), (31, 95, 1000)):
+        a = torch.randn((B, 3, n), device="cuda", generator=g)
+        b = torch.randn((B, 3, m), device="cuda", generator=g)
+        assert_same(a, b, 5)

@@ -1,5 +1,5 @@
-"""k-NN alone on the bench workload (32 x 1024 self query, k = 20): brute force vs the pruned search.
-   python tools/bench_knn.py            (RI_KNN_QPC=32|64|128 selects the queries per CTA of the pruned kernel)"""
+"""k-NN alone on the bench workload (32 x 1024 self query, k = 20): the thread-per-query kernel vs the warp-per-query kernel.
+   python tools/bench_knn.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -13,8 +13,6 @@ sets = []
 for q in range(3):
     x = torch.from_numpy(synth.make_clouds(B, N, seed=1000 + q)[:, :3].copy()).to(dev).contiguous()
     sets.append((x, torch.empty((B, k, N), device=dev), torch.empty((B, k, N), dtype=torch.int32, device=dev)))
-nws = L.ri_knn_workspace_bytes(B, N, N)
-ws = torch.empty(nws, dtype=torch.uint8, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 
 
@@ -26,11 +24,6 @@ def warp(i):
 def brute(i):
     x, d, ix = sets[i % 3]
     assert L.ri_knn_thread_f32(x.data_ptr(), x.data_ptr(), B, 3, N, N, k, d.data_ptr(), ix.data_ptr(), st) == 0
-
-
-def pruned(i):
-    x, d, ix = sets[i % 3]
-    assert L.ri_knn_ws_f32(x.data_ptr(), x.data_ptr(), B, 3, N, N, k, d.data_ptr(), ix.data_ptr(), ws.data_ptr(), nws, st) == 0
 
 
 def timeit(fn, steps=200):
@@ -51,5 +44,3 @@ warp(0); torch.cuda.synchronize()
 print("warp-per-query equal to brute force:", torch.equal(ref[0][1], sets[0][2]) and torch.equal(ref[0][0], sets[0][1]))
 print("brute  %.1f us" % timeit(brute))
 print("warp   %.1f us" % timeit(warp))
-if os.environ.get("RI_BENCH_PRUNED"):
-    print("pruned %.1f us (QPC=%s)" % (timeit(pruned), os.environ.get("RI_KNN_QPC", "64")))
