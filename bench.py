@@ -1,30 +1,41 @@
 #!/usr/bin/env python
 """bench.py — feature-extractor front-end throughput (points/sec on 1024-point clouds) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cu_dg|sph_dg] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sph_dg|cu_dg|...] [--impl ours|reference] [--only]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus N --steps K --warmup W
 
 A "step" is one pass of the front end (k-NN -> fused gather+PPF; coordinate prologue ->
 voxelize -> trilinear devoxelize -> DGCNN voxel-neighbour edge features) over one batch of 32 synthetic
-ModelNet40-shaped clouds of 1024 points PER GPU (weak scaling: clouds are sharded by rank, no data-path collective).
+ModelNet40-shaped clouds of 1024 points PER GPU (weak scaling: clouds are sharded by rank, no data-path collective; at
+N > 1 every step's per-point voxel indices are all-gathered over NCCL inside the timed region — the result gather).
 
-Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+The line's own numbers are BASELINE.json configs[0] (sph_dg: spherical voxelization r = 32, C = 67 — the configuration the
+north-star target is stated on).  The other BASELINE configurations are measured in the same run and reported under
+`also`: configs[1] cu_dg, configs[4] the spherical resolution sweep r = 16 / 64, configs[2] the registration job
+(front end on both clouds of a pair -> fixed random MLP -> tcgen05 mutual-NN matcher -> RANSAC -> metrics).
+
+Timed regions last >= 200 ms whatever --steps says: the K-step loop is repeated `reps` times between one pair of CUDA
+events and `ms_per_step` is the mean over K * reps steps (`timed_steps`).
+
+Keys beyond the base contract:
   roofline      dominant HBM kernel (vox_fill: the dense [C, r^3] grid + count grid written exactly once), algorithmic
                 bytes per launch / CUDA-event duration measured live, against MEASURED_PEAKS.json's HBM GB/s; the whole
-                voxelize op and the whole step are quoted beside it
+                voxelize op, the devoxelizer and the whole step are quoted beside it
   cpu_baseline  the C oracle port (oracle/ri_oracle.c, OpenMP over clouds) timed on this box's host cores on a
                 bounded sample of the same workload (rank 0, N=1 only)
   e2e           the same metric through the host-facing streaming call FrontEndPipeline.submit()/result(): every step
                 copies its inputs pinned host -> device and its per-point outputs device -> pinned host; the copies of
-                neighbouring steps overlap the compute (wall clock over K steps incl. the final drain); the
-                one-call-at-a-time FrontEnd.run_staged() figure is quoted beside it
+                neighbouring steps overlap the compute (wall clock incl. the final drain)
 `--impl reference` times the UNMODIFIED reference kernels (oracle/_ref, the reference's own CUDA backend recompiled
 for sm_100a — the reference has no CPU implementation: every op CHECK_CUDAs) through the reference's op sequence on
-the same workload with the same host<->device copies; if that library is absent it times the oracle port on the host.
+the same workload with the same host<->device copies, one rank per GPU like the other arm; if that library is absent
+it times the oracle port on the host.
 """
 import argparse
+import importlib.util
 import json
+import math
 import os
 import subprocess
 import sys
@@ -32,27 +43,45 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "point-cloud-registration-based-on-rotation-invariant-feature_b200")
 sys.path.insert(0, ROOT)
 
 METRIC = "feature-extractor points/sec (1024-pt clouds)"
 UNIT = "points/s"
 WORKLOADS = {
-    # BASELINE.json configs[1]: cu_dg variant (cube voxelization + DGCNN), 32 x 1024 on 1 B200; C = 3 + 4 + 64
-    # input channels of the registration model's first PVConv
-    "cu_dg": dict(voxel_shape="cube", B=32, N=1024, C=71, k=20, r=32,
-                  name="cu_dg front end: 32 x 1024 pts with normals, k=20 KNN+PPF, cube voxelize r=32 C=71, "
-                       "trilinear devox, DGCNN edge gather (BASELINE configs[1])"),
-    # BASELINE.json configs[0]: sph_dg classification front end; C = 3 + 64
+    # BASELINE.json configs[0]: sph_dg classification front end; C = 3 + 64 channels into PVConv-1
     "sph_dg": dict(voxel_shape="spherical", B=32, N=1024, C=67, k=20, r=32,
                    name="sph_dg front end: 32 x 1024 pts with normals, k=20 KNN+PPF, spherical voxelize r=32 C=67, "
                         "spherical trilinear devox, DGCNN edge gather (BASELINE configs[0])"),
+    # BASELINE.json configs[1]: cu_dg variant (cube voxelization + DGCNN), 32 x 1024 on 1 B200; C = 3 + 4 + 64
+    "cu_dg": dict(voxel_shape="cube", B=32, N=1024, C=71, k=20, r=32,
+                  name="cu_dg front end: 32 x 1024 pts with normals, k=20 KNN+PPF, cube voxelize r=32 C=71, "
+                       "trilinear devox, DGCNN edge gather (BASELINE configs[1])"),
 }
 # BASELINE.json configs[4]: throughput sweep over the spherical resolution (4096 clouds x 1024 pts = 128 steps of 32 clouds)
 for _r in (16, 64):
     WORKLOADS["sph_r%d" % _r] = dict(voxel_shape="spherical", B=32, N=1024, C=67, k=20, r=_r,
                                      name="sph_dg front end at spherical res %d: 32 x 1024 pts per step, k=20 KNN+PPF, C=67 "
                                           "(BASELINE configs[4] sweep)" % _r)
-RING = 3          # independent input/output buffer sets cycled between timed steps (footprint > L2)
+RING = 3            # independent input/output buffer sets cycled between timed steps (footprint > L2)
+MIN_TIMED_MS = 250  # every timed region lasts at least this long
+E2E_DEPTH = 4       # slots of the host-facing pipeline (tools/exp_e2e.py: 2 / 3 / 4 / 6 slots -> 0.578 / 0.579 / 0.547 / 0.552 ms per step)
+
+
+def config_for(wl, world):
+    """The `config` object: identical in both arms."""
+    return {"workload": wl["name"], "clouds_per_gpu": wl["B"], "points_per_cloud": wl["N"], "k": wl["k"],
+            "resolution": wl["r"], "channels": wl["C"], "voxel_shape": wl["voxel_shape"],
+            "parallelism": "clouds sharded by rank (dp%d)" % world,
+            "l2": "inputs larger than L2: %d independent batches cycled" % RING}
+
+
+def load_by_path(name, filename):
+    """Import one module of the package by file path (the reference arm must not load libri_b200.so)."""
+    spec = importlib.util.spec_from_file_location(name, os.path.join(PKG, filename))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def measured_peaks():
@@ -101,7 +130,7 @@ class ClockSampler:
         inside = [s for s in self.samples if any(a <= s[0] <= b for a, b in windows)]
         note = "sampled inside the timed regions"
         if not inside:
-            inside, note = self.samples, "timed regions shorter than the 100 ms sampling period: whole-run samples"
+            inside, note = self.samples, "no sample fell inside a timed region: whole-run samples"
         mhz = sorted(s[1] for s in inside)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for s in inside for n, v in zip(names, s[3]) if v.lower().startswith("active")})
@@ -109,125 +138,157 @@ class ClockSampler:
                 "samples": len(inside), "note": note}
 
 
-def traffic_from_profile(workload):
-    """dram bytes per launch of the dominant op from the committed ncu capture, if one exists (else null)."""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
+def traffic_from_profile(key):
+    """dram bytes per launch from the committed ncu capture (profiles/traffic.json), if one exists (else null)."""
     try:
-        return json.load(open(p)).get(workload)
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(key)
     except Exception:
         return None
 
 
-def step_traffic_from_profile(workload):
-    """dram bytes of ALL kernels of one step from the committed ncu capture (a lower bound of the HBM traffic), or null."""
-    return traffic_from_profile(workload + "_step_total")
+def reps_for(ms_estimate, steps):
+    return max(1, int(math.ceil(MIN_TIMED_MS / max(ms_estimate * steps, 1e-6))))
 
 
 # ===================================================================================================== ours
-def run_ours(args, rank, world, local):
+class Harness:
+    """Barrier + CUDA events + max over ranks around a callable that enqueues `steps` steps."""
+
+    def __init__(self, torch, shard, dev, world):
+        self.torch, self.shard, self.dev, self.world = torch, shard, dev, world
+        self.windows = []
+
+    def barrier(self):
+        if self.world > 1:
+            self.torch.distributed.barrier()
+
+    def timed(self, body, steps, probe=3):
+        """body(n) enqueues n steps.  Returns (ms per step over steps * reps steps, steps * reps)."""
+        torch = self.torch
+        def once(n):
+            self.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.time()
+            e0.record()
+            body(n)
+            e1.record()
+            torch.cuda.synchronize(); self.barrier()
+            return self.shard.max_over_ranks(e0.elapsed_time(e1), self.dev), (t0, time.time())
+        est, _ = once(max(probe, 1))
+        reps = reps_for(est / max(probe, 1), steps)
+        if self.world > 1:                                   # every rank must loop the same number of times
+            reps = int(self.shard.max_over_ranks(reps, self.dev))
+        ms, w = once(steps * reps)
+        self.windows.append(w)
+        return ms / (steps * reps), steps * reps
+
+
+def measure_workload(key, args, ri_b200, H, rank, world, local, headline):
     import numpy as np
-    import torch
-    import ri_b200
-    from ri_b200 import shard, synth
-
-    wl = WORKLOADS[args.workload]
+    torch = H.torch
+    synth, shard = ri_b200.synth, ri_b200.shard
+    wl = WORKLOADS[key]
     B, N, C, k, r = wl["B"], wl["N"], wl["C"], wl["k"], wl["r"]
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    sampler = ClockSampler(local) if rank == 0 else None
-
-    # per-rank shard of the (world * B)-cloud job, RING independent batches
+    dev = H.dev
     engines, batches = [], []
     for q in range(RING):
         pts = synth.make_clouds(B, N, seed=1000 + 17 * rank + q)
         feats = synth.make_features(B, C, N, seed=1000 + 17 * rank + q)
-        # throughput configuration (batches in flight): the per-cloud mean stays torch's kernel — with the mean fused into the
-        # prefix kernel a single step is 7 us shorter but three steps in flight are 4 us per step slower (measured)
-        fe = ri_b200.FrontEnd(B, N, C, k=k, r=r, voxel_shape=wl["voxel_shape"], normalize=False, device=dev, fuse_mean=False)
+        fe = ri_b200.FrontEnd(B, N, C, k=k, r=r, voxel_shape=wl["voxel_shape"], normalize=False, device=dev,
+                              fuse_mean=args.fuse_mean_in_flight)
         fe.h_points.copy_(torch.from_numpy(pts)); fe.h_features.copy_(torch.from_numpy(feats))
         fe.load(fe.h_points, fe.h_features)
         engines.append(fe); batches.append((pts, feats))
     torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-
-    def timed(fn, steps):
-        barrier(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.time()
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
-        torch.cuda.synchronize(); barrier()
-        return shard.max_over_ranks(e0.elapsed_time(e1), dev), (t0, time.time())
-
-    windows = []
-    # ---- device-resident throughput (`value`)
-    #      RING steps in flight (FrontEndLanes: engine q replays on its own launch stream, so the latency-bound prefix
-    #      and the k-NN of one batch run under the grid write / devoxelize of another); all K steps are launched after
-    #      the start event and have finished before the end event.  The one-step-at-a-time figure is quoted beside it.
     for i in range(max(args.warmup, RING)):
         engines[i % RING].forward()
-    # one step at a time: the latency configuration (mean fused into the prefix kernel)
+    torch.cuda.synchronize()
+
+    # ---- one step at a time (latency configuration: the mean fused into the prefix kernel)
     serial = []
     for q in range(RING):
         fe = ri_b200.FrontEnd(B, N, C, k=k, r=r, voxel_shape=wl["voxel_shape"], normalize=False, device=dev)
         fe.load(engines[q].h_points, engines[q].h_features); fe.forward(); serial.append(fe)
     torch.cuda.synchronize()
-    ms_single, w = timed(lambda i: serial[i % RING].forward(), args.steps); windows.append(w)
+    ms_single, _ = H.timed(lambda n: [serial[i % RING].forward() for i in range(n)], args.steps)
     serial_fused_mean = bool(serial[0]._own_mean)
     del serial
-    lanes = ri_b200.FrontEndLanes(engines, lanes=RING)
 
-    def timed_lanes(steps):
-        barrier(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.time()
-        e0.record()
+    # ---- device-resident throughput (`value`): RING steps in flight (FrontEndLanes: engine q replays on its own launch
+    #      stream, so the latency-bound prefix and the k-NN of one batch run under the grid write / devoxelize of
+    #      another); every step is launched after the start event and has finished before the end event.  At N > 1 each
+    #      step's voxel indices ([B,N] int32) are all-gathered over NCCL behind the step: the result gather.
+    lanes = ri_b200.FrontEndLanes(engines, lanes=RING)
+    gathered = [torch.empty((world * B, N), dtype=torch.int32, device=dev) for _ in range(RING)] if world > 1 else None
+    gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+
+    def lane_steps(n):
         lanes.begin()
-        for i in range(steps):
+        for i in range(n):
             lanes.forward(i)
+            if world > 1:
+                q = i % RING
+                gather_stream.wait_event(lanes._done[q])
+                with torch.cuda.stream(gather_stream):
+                    torch.distributed.all_gather_into_tensor(gathered[q], engines[q].ind)
         lanes.end()
-        e1.record()
-        torch.cuda.synchronize(); barrier()
-        return shard.max_over_ranks(e0.elapsed_time(e1), dev), (t0, time.time())
-    timed_lanes(max(args.warmup, RING))
-    ms, w = timed_lanes(args.steps); windows.append(w)
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(gather_stream)
+    lane_steps(max(args.warmup, RING))
+    ms, timed_steps = H.timed(lane_steps, args.steps)
     pts_per_step = world * B * N
-    value = pts_per_step * args.steps / (ms * 1e-3)
+    value = pts_per_step / (ms * 1e-3)
+    alg = engines[0].algorithmic_bytes()
+    peak, peak_src = measured_peaks()
+    step_gbs = alg["total"] / (ms * 1e-3) / 1e9
+    out = {"workload": wl["name"], "value": value, "ms_per_step": ms, "timed_steps": timed_steps,
+           "one_step_at_a_time": {"ms_per_step": ms_single, "value": pts_per_step / (ms_single * 1e-3),
+                                  "mean_fused_into_prefix_kernel": serial_fused_mean},
+           "whole_step": {"algorithmic_bytes": alg["total"], "achieved": step_gbs, "frac": step_gbs / peak}}
 
     # ---- end to end through the host-facing call (`e2e`): every step copies ITS inputs from pinned host memory to the
-    #      device and ITS per-point outputs back to pinned host memory; the streaming API overlaps the copies of
-    #      neighbouring steps with the compute (FrontEndPipeline), the one-call-at-a-time form is quoted beside it
-    for i in range(max(3, min(args.warmup, 5))):
-        engines[i % RING].run_staged()
-    e2e_steps = max(1, min(args.steps, 200))
-    ms_sync, w = timed(lambda i: engines[i % RING].run_staged(), e2e_steps); windows.append(w)
-    pipe = ri_b200.FrontEndPipeline(B, N, C, depth=RING, k=k, r=r, voxel_shape=wl["voxel_shape"], normalize=False, device=dev)
-    for q in range(RING):
-        pipe.slot(q).h_points.copy_(torch.from_numpy(batches[q][0])); pipe.slot(q).h_features.copy_(torch.from_numpy(batches[q][1]))
-
-    def pipe_step(i):
+    #      device and ITS per-point outputs back to pinned host memory (ppf, devox, the feat - mean(cell) half of the
+    #      edge features; the other half of that tensor is the caller's own input and is not shipped back); the
+    #      streaming API overlaps the copies of neighbouring steps with the compute
+    pipe = ri_b200.FrontEndPipeline(B, N, C, depth=E2E_DEPTH, k=k, r=r, voxel_shape=wl["voxel_shape"], normalize=False,
+                                    device=dev, edge_echo=False)
+    for q in range(E2E_DEPTH):
+        pipe.slot(q).h_points.copy_(torch.from_numpy(batches[q % RING][0])); pipe.slot(q).h_features.copy_(torch.from_numpy(batches[q % RING][1]))
+    for i in range(2 * E2E_DEPTH):
         pipe.submit(pipe.acquire())
-    for i in range(2 * RING):
-        pipe_step(i)
     pipe.drain()
-    barrier(); torch.cuda.synchronize()
-    t0 = time.time(); p0 = time.perf_counter()
-    for i in range(e2e_steps):
-        pipe_step(i)
-    pipe.drain()
-    torch.cuda.synchronize()
-    ms_e2e = shard.max_over_ranks((time.perf_counter() - p0) * 1e3, dev); windows.append((t0, time.time()))
-    barrier()
-    e2e_value = pts_per_step * e2e_steps / (ms_e2e * 1e-3)
+
+    def e2e_once(n):
+        H.barrier(); torch.cuda.synchronize()
+        t0 = time.time(); p0 = time.perf_counter()
+        for i in range(n):
+            pipe.submit(pipe.acquire())
+        pipe.drain()
+        torch.cuda.synchronize()
+        el = shard.max_over_ranks((time.perf_counter() - p0) * 1e3, dev)
+        H.barrier()
+        return el, (t0, time.time())
+    est, _ = e2e_once(5)
+    e2e_steps = max(args.steps, int(math.ceil(MIN_TIMED_MS / max(est / 5, 1e-6))))
+    if world > 1:
+        e2e_steps = int(shard.max_over_ranks(e2e_steps, dev))
+    ms_e2e, w = e2e_once(e2e_steps); H.windows.append(w)
+    ms_e2e /= e2e_steps
+    out["e2e"] = {"value": pts_per_step / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": pipe.slot(0).h2d_bytes,
+                  "d2h_bytes_per_step": pipe.slot(0).d2h_bytes, "steps": e2e_steps, "ms_per_step": ms_e2e,
+                  "api": "FrontEndPipeline.submit/result (%d slots: H2D, step and D2H of neighbouring steps overlap; one copy per direction and step); outputs " % E2E_DEPTH +
+                         "ppf [B,4,k,N], devox [B,C,N], edge_rel [B,C,N]"}
+    if headline:
+        for i in range(3):
+            engines[i % RING].run_staged()
+        ms_sync, n_sync = H.timed(lambda n: [engines[i % RING].run_staged() for i in range(n)], min(args.steps, 50))
+        out["e2e"]["one_call_at_a_time"] = {"value": pts_per_step / (ms_sync * 1e-3), "ms_per_step": ms_sync,
+                                            "api": "FrontEnd.run_staged() (full edge tensor [B,2C,N] shipped back)",
+                                            "d2h_bytes_per_step": engines[0].d2h_bytes}
     del pipe
 
-    # ---- dominant HBM kernel in isolation: vox_fill (the dense [C, r^3] grid + count grid written once), and the whole
-    #      voxelize op (prefix + fill), CUDA events on the launching stream
+    # ---- the HBM kernels in isolation (CUDA events on the launching stream): vox_fill (the dense [C, r^3] grid + count
+    #      grid written once), the devoxelizer, and the whole voxelize op (prefix + fill)
     L = ri_b200._lib.lib
     st = torch.cuda.current_stream().cuda_stream
     shape_id = 2 if wl["voxel_shape"] == "spherical" else 0
@@ -241,114 +302,165 @@ def run_ours(args, rank, world, local):
         fe = engines[i % RING]
         mean = fe._mean_buf if fe._own_mean else fe.points[:, :3, :].mean(2)
         rc = L.ri_vox_front_f32(fe.points.data_ptr(), 6, mean.data_ptr(), fe.features.data_ptr(), B, C, N, r, shape_id, 0.0,
-                                fe.NORM_MODE | (0x100 if fe._own_mean else 0), fe.norm_coords.data_ptr(), fe._vox_coords.data_ptr(), fe.ind.data_ptr(),
+                                fe._front_mode(fe._own_mean), fe.norm_coords.data_ptr(), fe._vox_coords.data_ptr(), fe.ind.data_ptr(),
                                 fe.edge.data_ptr(), fe._ws.data_ptr(), fe._ws_bytes, st)
         assert rc == 0
         fill_only(i)
     for i in range(RING):
         vox_op(i)
-    vox_steps = max(3, min(args.steps, 300))
-    ms_fill, w = timed(fill_only, vox_steps); windows.append(w)
-    ms_devox, w = timed(lambda i: engines[i % RING]._devox(0, B, st), vox_steps); windows.append(w)
-    ms_vox, w = timed(vox_op, vox_steps); windows.append(w)
-    alg = engines[0].algorithmic_bytes()
-    peak, peak_src = measured_peaks()
+    ms_fill, _ = H.timed(lambda n: [fill_only(i) for i in range(n)], args.steps)
+    ms_devox, _ = H.timed(lambda n: [engines[i % RING]._devox(0, B, st) for i in range(n)], args.steps)
+    ms_vox, _ = H.timed(lambda n: [vox_op(i) for i in range(n)], args.steps)
+    ms_knn, _ = H.timed(lambda n: [engines[i % RING]._knn() for i in range(n)], args.steps)
     fill_bytes = B * (4 * (r ** 3) + 4 * C * (r ** 3))
-    fill_gbs = fill_bytes / (ms_fill / vox_steps * 1e-3) / 1e9
-    vox_gbs = alg["voxelize"] / (ms_vox / vox_steps * 1e-3) / 1e9
-    step_gbs = alg["total"] / (ms / args.steps * 1e-3) / 1e9
-    step_traffic = step_traffic_from_profile(args.workload)
+    fill_gbs = fill_bytes / (ms_fill * 1e-3) / 1e9
+    vox_gbs = alg["voxelize"] / (ms_vox * 1e-3) / 1e9
+    devox_gbs = alg["devox"] / (ms_devox * 1e-3) / 1e9
+    step_traffic = traffic_from_profile(key + "_step_total")
+    out["roofline"] = {
+        "bound": "hbm", "kernel": "vox_fill (dense [C,r^3] grid + count grid, written once)",
+        "achieved": fill_gbs, "peak": peak, "unit": "GB/s", "frac": fill_gbs / peak,
+        "traffic": traffic_from_profile(key), "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": fill_bytes, "ms_per_launch": ms_fill,
+        "voxelize_op": {"kernels": ("vox_front (mean, prologue, cell sort, cell means, edge features) + vox_fill" if engines[0]._own_mean
+                                    else "torch mean + vox_front (prologue, cell sort, cell means, edge features) + vox_fill"),
+                        "algorithmic_bytes": alg["voxelize"], "ms": ms_vox, "achieved": vox_gbs, "frac": vox_gbs / peak},
+        "devoxelize_op": {"algorithmic_bytes": alg["devox"], "ms": ms_devox, "achieved": devox_gbs, "frac": devox_gbs / peak,
+                          "grid_bytes": B * 4 * C * r ** 3, "traffic": traffic_from_profile(key + "_devox")},
+        "knn_op": {"kernel": "split + knn3_warp_kernel (one warp per query, exact threshold selection)", "ms": ms_knn},
+        "whole_step": dict(out["whole_step"], dram_traffic=step_traffic,
+                           dram_traffic_frac=(step_traffic / (ms * 1e-3) / 1e9 / peak) if step_traffic else None)}
+    out["gpu_launches_per_step"] = engines[0].kernels_per_step
+    out["_engine_meta"] = {"grid_chunks": engines[0].grid_chunks, "mean_in_flight_fused": bool(engines[0]._own_mean)}
+    out["_batch0"] = batches[0]
+    del lanes, engines
+    torch.cuda.empty_cache()
+    return out
 
-    # ---- registration matcher (BASELINE configs[2]: 256 pairs x 1024 x 1024 x 512 over 8 GPUs = 32 pairs per GPU), an
-    #      auxiliary figure: tcgen05 3xTF32 contraction + fused argmins, CUDA events, descriptors resident in HBM
+
+def measure_registration(ri_b200, H, rank, world):
+    """BASELINE configs[2]: 256 source/target pairs x 1024 pts over the GPUs of the box = 256 / world pairs per GPU:
+    front end on both clouds of every pair (k-NN + PPF) -> descriptors = a FIXED random two-layer MLP on each point's
+    sorted-neighbour point-pair features (stand-in for the dense layers, which are out of scope; rigid-motion invariant like
+    the real descriptor) -> tcgen05 mutual-NN matcher -> RANSAC + Horn refit -> RRE / RTE / RMSE -> one all-gather."""
+    import numpy as np
+    torch = H.torch
+    synth, shard = ri_b200.synth, ri_b200.shard
+    dev = H.dev
+    PAIRS, N, k, Cd = 256, 1024, 20, 512
+    lo, hi = shard.shard_range(PAIRS, rank, world)
+    P = hi - lo
+    src, tgt, R, t = synth.make_pairs(PAIRS, N, seed=2024)
+    src, tgt, R, t = src[lo:hi], tgt[lo:hi], R[lo:hi], t[lo:hi]
+    both = torch.from_numpy(np.concatenate([src, tgt], 0)).to(dev).contiguous()            # [2P,6,N]
+    g = torch.Generator(device=dev); g.manual_seed(7)
+    W1 = torch.randn((128, 4 * k), device=dev, generator=g) / (4 * k) ** 0.5
+    W2 = torch.randn((Cd, 128), device=dev, generator=g) / 128 ** 0.5
+    gt = torch.eye(4, device=dev)[None].repeat(P, 1, 1)
+    gt[:, :3, :3] = torch.from_numpy(R).to(dev); gt[:, :3, 3] = torch.from_numpy(t).to(dev)
+    p1 = both[:P, :3].transpose(1, 2).contiguous(); p2 = both[P:, :3].transpose(1, 2).contiguous()
+    mm = ri_b200.matcher.MutualMatcher(P, Cd, N, N, device=dev)
+
+    def step():
+        xyz = both[:, :3].contiguous(); nrm = both[:, 3:].contiguous()
+        _, _, ppf = torch.ops.ri.knn_ppf(xyz, nrm, k)                                       # [2P,4,k,N]
+        f = torch.tanh(torch.einsum("oc,bcn->bon", W1, ppf.reshape(2 * P, 4 * k, N)))
+        f = torch.einsum("oc,bcn->bon", W2, f).contiguous()                                 # [2P,512,N]
+        m = mm(f[:P], f[P:])
+        T, inl = ri_b200.registration.estimate_poses(p1, p2, m.idx1, m.idx2, m.count, func="ransac", seed=1)
+        met = ri_b200.registration.registration_metrics(gt, T, p1)
+        res = torch.cat([T.reshape(P, 16).double(), met, inl[:, None].double(), m.count[:, None].double()], 1)
+        return shard.gather_clouds(res, PAIRS)
+    try:
+        full = None
+        for _ in range(3):
+            full = step()
+        ms, n = H.timed(lambda n: [step() for _ in range(n)], 5, probe=2)
+    except Exception as e:                                                                  # never take the headline down
+        return {"error": repr(e)[:300]}
+    full = full.cpu().numpy()
+    return {"workload": "DeepGMR-shaped registration job (BASELINE configs[2]): %d pairs x %d pts, %d per GPU; front end (k-NN + PPF) "
+                        "on both clouds -> fixed random MLP to %d-d descriptors -> mutual-NN matcher -> RANSAC + refit -> "
+                        "metrics -> all_gather" % (PAIRS, N, P, Cd),
+            "ms_per_job": ms, "pairs_per_s": PAIRS / (ms * 1e-3), "timed_jobs": n,
+            "mean_mutual_matches": float(full[:, 20].mean()), "mean_inliers": float(full[:, 19].mean()),
+            "rre_deg_median": float(np.median(full[:, 16])), "recall_rmse_lt_0.2": float((full[:, 18] < 0.2).mean())}
+
+
+def measure_matcher(ri_b200, H, rank, world):
+    """The matcher alone (row a11): 32 pairs x 1024 x 1024 x 512 per GPU, descriptors resident in HBM."""
+    torch = H.torch
+    dev = H.dev
     MP, MC, Mn = 32, 512, 1024
     g = torch.Generator(device=dev); g.manual_seed(4242 + rank)
     d1 = torch.randn((MP, MC, Mn), device=dev, generator=g); d2 = torch.randn((MP, MC, Mn), device=dev, generator=g)
     mm = ri_b200.matcher.MutualMatcher(MP, MC, Mn, Mn, device=dev)
     for _ in range(3):
         mm(d1, d2)
-    m_steps = 20
-    ms_match, w = timed(lambda i: mm(d1, d2), m_steps); windows.append(w)
-    ms_match /= m_steps
-    # ... and what follows it on the GPU (row f3): RANSAC (1000 hypotheses per pair) + Horn refit + RRE/RTE/RMSE
-    src_p, tgt_p, Rg, tg = synth.make_pairs(MP, Mn, seed=77 + rank)
-    p1 = torch.from_numpy(np.ascontiguousarray(src_p[:, :3].transpose(0, 2, 1))).to(dev)
-    p2 = torch.from_numpy(np.ascontiguousarray(tgt_p[:, :3].transpose(0, 2, 1))).to(dev)
-    ident = torch.arange(Mn, dtype=torch.int32, device=dev)[None].repeat(MP, 1).contiguous()
-    cnt_p = torch.full((MP,), Mn, dtype=torch.int32, device=dev)
-    gt_T = torch.eye(4, device=dev)[None].repeat(MP, 1, 1); gt_T[:, :3, :3] = torch.from_numpy(Rg).to(dev); gt_T[:, :3, 3] = torch.from_numpy(tg).to(dev)
+    ms, n = H.timed(lambda n: [mm(d1, d2) for _ in range(n)], 20)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    useful = world * 2.0 * MP * Mn * Mn * MC / (ms * 1e-3) / 1e12
+    return {"workload": "mutual-NN matching, %d pairs x %d x %d x %d per GPU" % (MP, Mn, Mn, MC),
+            "pairs_per_s": world * MP / (ms * 1e-3), "ms_per_call": ms, "timed_calls": n,
+            "useful_tflops": useful, "issued_tf32_tflops": 3 * useful,
+            "frac_of_bf16_sustained": (useful / world / peaks["bf16_tflops_sustained"]) if "bf16_tflops_sustained" in peaks else None,
+            "note": "3xTF32 split precision on tcgen05: three tensor-core products per useful one (ceiling 1/6 of the bf16 "
+                    "peak); includes the fp32 distance re-evaluation of the matches"}
 
-    def pose_step(i):
-        T, _ = ri_b200.registration.estimate_poses(p1, p2, ident, ident, cnt_p, func='ransac', seed=i)
-        return ri_b200.registration.registration_metrics(gt_T, T, p1)
-    for _ in range(3):
-        pose_step(0)
-    ms_pose, w = timed(pose_step, m_steps); windows.append(w)
-    ms_pose /= m_steps
-    pose_rre = float(pose_step(0)[:, 0].max())
-    del mm, d1, d2
 
+def run_ours(args, rank, world, local):
+    import torch
+    import ri_b200
+    from ri_b200 import shard
+
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    numa = shard.bind_host_to_gpu(local)            # before any pinned allocation
+    sampler = ClockSampler(local) if rank == 0 else None
+    H = Harness(torch, shard, dev, world)
+
+    head = measure_workload(args.workload, args, ri_b200, H, rank, world, local, headline=True)
+    also = {}
+    if not args.only:
+        for key in ("cu_dg", "sph_dg", "sph_r16", "sph_r64"):
+            if key == args.workload:
+                continue
+            m = measure_workload(key, args, ri_b200, H, rank, world, local, headline=False)
+            m.pop("_batch0"); m.pop("_engine_meta")
+            also[key] = m
+        also["matcher"] = measure_matcher(ri_b200, H, rank, world)
+        also["registration_job"] = measure_registration(ri_b200, H, rank, world)
     if rank != 0:
         return
     sampler.stop()
+    wl = WORKLOADS[args.workload]
+    meta = head.pop("_engine_meta")
+    batch0 = head.pop("_batch0")
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "clouds_per_gpu": B, "points_per_cloud": N, "k": k, "resolution": r,
-                   "channels": C, "voxel_shape": wl["voxel_shape"], "parallelism": "clouds sharded by rank (dp%d)" % world,
-                   "l2": "inputs larger than L2: %d independent batches cycled, %.0f MB written per step" %
-                         (RING, (alg["voxelize"] + alg["devox"] + alg["edge"] + alg["knn_ppf"]) / 1e6),
-                   "cuda_graph": True,
-                   "overlap": "k-NN/PPF branch on a side stream next to the grid writer and the devoxelizer; %d independent "
-                              "batches in flight on %d launch streams" % (RING, RING),
-                   "steps_in_flight": RING,
-                   "one_step_at_a_time": {"ms_per_step": ms_single / args.steps,
-                                          "value": pts_per_step * args.steps / (ms_single * 1e-3),
-                                          "mean_fused_into_prefix_kernel": serial_fused_mean},
-                   "grid_chunks": engines[0].grid_chunks},
-        "roofline": {"bound": "hbm", "kernel": "vox_fill (dense [C,r^3] grid + count grid, written once)",
-                     "achieved": fill_gbs, "peak": peak, "unit": "GB/s", "frac": fill_gbs / peak,
-                     "traffic": traffic_from_profile(args.workload), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": fill_bytes, "ms_per_launch": ms_fill / vox_steps,
-                     "voxelize_op": {"kernels": ("vox_front (mean, prologue, cell sort, cell means, edge features) + vox_fill" if engines[0]._own_mean
-                                                 else "torch mean + vox_front (prologue, cell sort, cell means, edge features) + vox_fill"),
-                                     "algorithmic_bytes": alg["voxelize"], "ms": ms_vox / vox_steps,
-                                     "achieved": vox_gbs, "frac": vox_gbs / peak},
-                     "devoxelize_op": {"kernel": "devox_stream (planes streamed by TMA through a shared-memory ring)"
-                                                 if not engines[0].join_before_devox else "devox (per-point gathers)",
-                                       "algorithmic_bytes": alg["devox"], "ms": ms_devox / vox_steps,
-                                       "achieved": alg["devox"] / (ms_devox / vox_steps * 1e-3) / 1e9,
-                                       "frac": alg["devox"] / (ms_devox / vox_steps * 1e-3) / 1e9 / peak,
-                                       "grid_bytes_read": B * 4 * C * r ** 3,
-                                       "note": "algorithmic bytes count 32 B per point and channel (8 corners); at r=32, N=1024 "
-                                               "the corners touch about every 32-byte sector, so the kernel reads the whole grid: "
-                                               "grid_bytes_read / ms is its real HBM rate"},
-                     "whole_step": {"algorithmic_bytes": alg["total"], "achieved": step_gbs, "frac": step_gbs / peak,
-                                    "dram_traffic": step_traffic,
-                                    "dram_traffic_gbs": (step_traffic / (ms / args.steps * 1e-3) / 1e9) if step_traffic else None,
-                                    "dram_traffic_frac": (step_traffic / (ms / args.steps * 1e-3) / 1e9 / peak) if step_traffic else None,
-                                    "note": "algorithmic bytes count the devoxelizer's 8 corners per point (32 B per point and "
-                                            "channel); at sector granularity it reads the whole grid, which dram_traffic (sum of "
-                                            "the kernels' dram bytes in the committed ncu capture, a lower bound) includes"}},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": engines[0].h2d_bytes,
-                "d2h_bytes_per_step": engines[0].d2h_bytes, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
-                "api": "FrontEndPipeline.submit/result (3 slots: H2D, step and D2H of neighbouring steps overlap)",
-                "one_call_at_a_time": {"value": pts_per_step * e2e_steps / (ms_sync * 1e-3), "ms_per_step": ms_sync / e2e_steps,
-                                       "api": "FrontEnd.run_staged()"}},
-        "gpu_launches": engines[0].kernels_per_step * args.steps,
-        "clocks": sampler.summary(windows),
-        "matcher": {"workload": "mutual-NN matching, %d pairs x %d x %d x %d per GPU (BASELINE configs[2] at 8 GPUs)" % (MP, Mn, Mn, MC),
-                    "pairs_per_s": world * MP / (ms_match * 1e-3), "ms_per_call": ms_match,
-                    "useful_tflops": world * 2.0 * MP * Mn * Mn * MC / (ms_match * 1e-3) / 1e12,
-                    "issued_tf32_tflops": world * 3 * 2.0 * MP * Mn * Mn * MC / (ms_match * 1e-3) / 1e12,
-                    "note": "3xTF32 split precision: three tensor-core products per useful one; includes the re-tiling "
-                            "pre-pass and the fp32 distance re-evaluation",
-                    "pose": {"workload": "RANSAC 1000 hypotheses + Horn refit + RRE/RTE/RMSE, %d pairs x %d matches per GPU" % (MP, Mn),
-                             "ms_per_call": ms_pose, "pairs_per_s": world * MP / (ms_pose * 1e-3), "max_rre_deg": pose_rre}},
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": head["ms_per_step"], "timed_steps": head["timed_steps"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_for(wl, world),
+        "notes": {"cuda_graph": True, "steps_in_flight": RING, "grid_chunks": meta["grid_chunks"],
+                  "overlap": "k-NN/PPF branch on a side stream next to the grid writer and the devoxelizer; %d independent "
+                             "batches in flight on %d launch streams" % (RING, RING),
+                  "one_step_at_a_time": head["one_step_at_a_time"],
+                  "result_gather": ("all_gather_into_tensor of every step's voxel indices [B,N] i32 over NCCL, inside the timed region"
+                                    if world > 1 else "single GPU: nothing to gather"),
+                  "host_numa_binding": numa,
+                  "timed_region": "K-step loop repeated until >= %d ms (timed_steps steps between one pair of CUDA events)" % MIN_TIMED_MS},
+        "roofline": head["roofline"],
+        "e2e": head["e2e"],
+        "gpu_launches": head["gpu_launches_per_step"] * head["timed_steps"],
+        "clocks": sampler.summary(H.windows),
+        "also": also,
     }
     if world == 1:
-        line["cpu_baseline"] = cpu_port_baseline(wl, batches[0])
+        line["cpu_baseline"] = cpu_port_baseline(wl, batch0)
     print(json.dumps(line))
 
 
@@ -388,22 +500,18 @@ def cpu_port_baseline(wl, batch, reps=3):
 
 # ================================================================================================ reference
 def run_reference(args, rank, world, local):
-    if rank != 0:
-        return
+    """The reference arm, one rank per GPU like the other arm: every rank runs the reference's unmodified CUDA kernels on its
+    own shard of the (world * B)-cloud job; value = all ranks' points / the slowest rank's time."""
     wl = WORKLOADS[args.workload]
     B, N, C, k, r = wl["B"], wl["N"], wl["C"], wl["k"], wl["r"]
     base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": wl["name"], "clouds_per_gpu": B, "points_per_cloud": N, "k": k,
-                                            "resolution": r, "channels": C, "voxel_shape": wl["voxel_shape"]}}
-    sys.path.insert(0, os.path.join(ROOT, "point-cloud-registration-based-on-rotation-invariant-feature_b200"))
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("ri_synth", os.path.join(
-        ROOT, "point-cloud-registration-based-on-rotation-invariant-feature_b200", "synth.py"))
-    synth = importlib.util.module_from_spec(spec); spec.loader.exec_module(synth)
-    pts = synth.make_clouds(B, N, seed=1000); feats = synth.make_features(B, C, N, seed=1000)
+            "data": "synthetic", "config": config_for(wl, world)}
+    synth = load_by_path("ri_synth", "synth.py")
+    pts = synth.make_clouds(B, N, seed=1000 + 17 * rank); feats = synth.make_features(B, C, N, seed=1000 + 17 * rank)
 
     ref = None
+    torch = None
     try:
         import torch
         from oracle.build_ref import load_ref
@@ -412,18 +520,26 @@ def run_reference(args, rank, world, local):
     except Exception:
         ref = None
 
-    if ref is None:                                       # no reference library on this box: the oracle port
+    if ref is None:                                       # no reference library on this box: the oracle port, rank 0 only
+        if rank != 0:
+            return
         cb = cpu_port_baseline(wl, (pts, feats), reps=max(1, min(args.steps, 3)))
-        base.update({"value": cb["value"], "ms_per_step": B * N / cb["value"] * 1e3, "cpu_baseline": cb,
+        base.update({"n_gpus": 1, "value": cb["value"], "ms_per_step": B * N / cb["value"] * 1e3, "cpu_baseline": cb,
                      "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         print(json.dumps(base))
         return
 
-    import torch
-    torch.cuda.set_device(0)
-    dev = "cuda:0"
+    shard = load_by_path("ri_shard", "shard.py")          # torch-only helpers; the product library stays unloaded
+    shard.init_from_env()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    numa = shard.bind_host_to_gpu(local)
     hp = torch.from_numpy(pts).pin_memory(); hf = torch.from_numpy(feats).pin_memory()
     out_h = {}
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
 
     def step(host):
         """Reference op sequence for the same front end, through the reference backend's own functions
@@ -450,51 +566,73 @@ def run_reference(args, rank, world, local):
         centre = avg.gather(2, it.unsqueeze(1).expand(-1, C, -1).long())
         rel = f - centre
         rel[mask.unsqueeze(1).expand(-1, C, -1)] = 0
-        edge = torch.cat((rel, f), 1)
+        edge = torch.cat((rel, f), 1)                                                      # what the next layer consumes
         if host:
-            for name, t in (("ppf", ppf), ("devox", dv), ("edge", edge)):
+            # the same three tensors the other arm ships back: ppf, devox, the relative half of the edge features
+            for name, t in (("ppf", ppf), ("devox", dv), ("edge_rel", rel)):
                 if name not in out_h:
                     out_h[name] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
                 out_h[name].copy_(t, non_blocking=True)
             torch.cuda.synchronize()
+        return edge
 
     d_p, d_f = hp.to(dev), hf.to(dev)
     for _ in range(max(args.warmup, 3)):
         step(False)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step(False)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+
+    def timed_events(n):
+        barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            step(False)
+        e1.record(); torch.cuda.synchronize(); barrier()
+        return shard.max_over_ranks(e0.elapsed_time(e1), dev)
+    est = timed_events(2) / 2
+    n1 = int(shard.max_over_ranks(max(args.steps, int(math.ceil(MIN_TIMED_MS / max(est, 1e-6)))), dev))
+    ms = timed_events(n1) / n1
     for _ in range(3):
         step(True)
-    n2 = max(1, min(args.steps, 50))
-    t0 = time.perf_counter()
-    for _ in range(n2):
-        step(True)
-    ms2 = (time.perf_counter() - t0) * 1e3
-    value = B * N * args.steps / (ms * 1e-3)
+
+    def timed_wall(n):
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            step(True)
+        el = shard.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
+        barrier()
+        return el
+    est2 = timed_wall(2) / 2
+    n2 = int(shard.max_over_ranks(max(min(args.steps, 50), int(math.ceil(MIN_TIMED_MS / max(est2, 1e-6)))), dev))
+    ms2 = timed_wall(n2) / n2
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    if rank != 0:
+        return
+    value = world * B * N / (ms * 1e-3)
     base.update({
-        "value": value, "ms_per_step": ms / args.steps,
+        "value": value, "ms_per_step": ms, "timed_steps": n1,
+        "notes": {"host_numa_binding": numa},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
                          "sample": "the reference's own CUDA kernels (oracle/_ref, unmodified sources recompiled for "
-                                   "sm_100a) on the same B200 — the reference has no CPU implementation of this path"},
-        "e2e": {"value": B * N * n2 / (ms2 * 1e-3), "unit": UNIT,
+                                   "sm_100a) on the same B200s, one rank per GPU — the reference has no CPU implementation "
+                                   "of this path"},
+        "e2e": {"value": world * B * N / (ms2 * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": hp.numel() * 4 + hf.numel() * 4,
-                "d2h_bytes_per_step": sum(t.numel() * 4 for t in out_h.values()), "steps": n2,
-                "ms_per_step": ms2 / n2}})
+                "d2h_bytes_per_step": sum(t.numel() * 4 for t in out_h.values()), "steps": n2, "ms_per_step": ms2}})
     print(json.dumps(base))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cu_dg")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="sph_dg")
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--only", action="store_true", help="measure only --workload (skip the `also` configurations)")
+    ap.add_argument("--fuse-mean-in-flight", dest="fuse_mean_in_flight", action="store_true", default=True)
+    ap.add_argument("--torch-mean-in-flight", dest="fuse_mean_in_flight", action="store_false")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 

@@ -151,7 +151,10 @@ int ri_voxelize_fill_f32(int B, int C, int N, int r, int b0, int b1, float* out,
 /* The prefix of the voxel branch in one launch: ri_vox_prologue_f32 + ri_*_voxelize_prepare_f32 + ri_voxelize_means_f32
  * for all B clouds (bit-identical outputs); ri_voxelize_fill_f32 then completes the voxelization.  Arguments as
  * ri_vox_prologue_f32 plus feat [B,C,N]; outputs norm_coords [B,3,N], vox_coords [B,3,N] (cube shapes), ind [B,N],
- * edge [B,2C,N] (nullable) and the workspace tables.  N <= 1024 and the tiled-path conditions, else RI_ERR_UNSUPPORTED. */
+ * edge [B,2C,N] (nullable) and the workspace tables.  N <= 1024 and the tiled-path conditions, else RI_ERR_UNSUPPORTED.
+ * norm_mode flag bits: 0x100 = compute the per-cloud mean inside the kernel (torch's reduction order; written to `mean`);
+ * 0x200 = `edge` is [B,C,N] and receives only the (feat - mean of the point's cell) half of the edge features — the
+ * other half is the caller's own input. */
 int ri_vox_front_f32(const float* points, int pstride, const float* mean, const float* feat,
                      int B, int C, int N, int r, int shape, float eps, int norm_mode,
                      float* norm_coords, int* vox_coords, int* ind, float* edge,

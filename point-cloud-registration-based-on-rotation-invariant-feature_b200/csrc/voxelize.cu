@@ -357,7 +357,7 @@ vox_front_kernel(const float* __restrict__ points, int pstride, float* __restric
     if (shape != 0) {
         float m = 0.f;
         for (int i = tid; i < N; i += kFrontThreads)
-            m = fmaxf(m, radius3(__fsub_rn(Pt[i], mx), __fsub_rn(Pt[i + N], my), __fsub_rn(Pt[i + 2 * (size_t)N], mz), norm_mode));
+            m = fmaxf(m, radius3(__fsub_rn(Pt[i], mx), __fsub_rn(Pt[i + N], my), __fsub_rn(Pt[i + 2 * (size_t)N], mz), norm_mode & 0xff));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         if ((tid & 31) == 0) sred[tid >> 5] = m;
@@ -511,13 +511,16 @@ vox_front_kernel(const float* __restrict__ points, int pstride, float* __restric
     }
     if (edge == nullptr) return;
     __syncthreads();
-    float* Eo = edge + ((size_t)b * 2 * C + c0) * N;
+    // rel_only (norm_mode bit 9): edge is [B,C,N] and receives the feat - mean half alone; the other half of the DGCNN
+    // edge tensor is the input itself, which a caller on the far side of a PCIe link already holds
+    const bool rel_only = (norm_mode & 0x200) != 0;
+    float* Eo = edge + ((size_t)b * (rel_only ? 1 : 2) * C + c0) * N;
     for (int e = tid; e < nch * N; e += kFrontThreads) {
         const int j = e / N, i = e - j * N;
         const int sg = ssegof[i];
         const float f = sfeat[j * ld + i];
         Eo[(size_t)j * N + i] = sg >= 0 ? __fsub_rn(f, smean[j * ucap + sg]) : 0.f;
-        Eo[((size_t)C + j) * N + i] = f;
+        if (!rel_only) Eo[((size_t)C + j) * N + i] = f;
     }
 }
 
@@ -1229,8 +1232,9 @@ extern "C" int ri_vox_front_f32(const float* points, int pstride, const float* m
     ri_prefer_step_carveout(kern);
     dim3 grid(C > 0 ? (C + kMeanChans - 1) / kMeanChans : 1, B);
     // norm_mode bit 8: compute the per-cloud mean inside the kernel (torch's reduction order) and write it to `mean`
+    // norm_mode bit 9: `edge` is [B,C,N] and receives only the feat - mean(cell) half of the edge features
     const int own_mean = (norm_mode & 0x100) != 0;
-    norm_mode &= 0xff;
+    norm_mode &= 0x2ff;
     if (own_mean && (N < 128 || (N & 3) != 0 || ((uintptr_t)points & 15) != 0)) return RI_ERR_UNSUPPORTED;
     const float mean_factor = (float)(3LL * B) / (float)(3LL * B * N);           // mean_kernel_cuda: num_outputs / numel
     kern<<<grid, kFrontThreads, smem, (cudaStream_t)stream>>>(points, pstride, const_cast<float*>(mean), own_mean, mean_factor,

@@ -37,7 +37,7 @@ class FrontEnd:
 
     def __init__(self, B, N, C, k=20, r=32, voxel_shape='spherical', normalize=False, eps=0.0,
                  device='cuda', use_graph=True, overlap=True, grid_chunks=None, devox_side_stream=True,
-                 knn_after_front=True, join_before_devox=None, fuse_mean=True):
+                 knn_after_front=True, join_before_devox=None, fuse_mean=True, edge_echo=True):
         if voxel_shape not in ('spherical', 'cube'):
             raise ValueError('voxel_shape must be "spherical" or "cube"')
         self.B, self.N, self.C, self.k, self.r = int(B), int(N), int(C), int(k), int(r)
@@ -46,6 +46,10 @@ class FrontEnd:
         if self.device.type != 'cuda':
             raise RuntimeError('FrontEnd runs on a CUDA device only (no CPU path exists)')
         self.use_graph, self.overlap = use_graph, overlap
+        # edge_echo=False: `edge` is [B,C,N] = feat - mean(cell) only.  The other half of the DGCNN edge tensor (pvconv.py:90:
+        # cat(rel, feat)) is the input itself; a host-side caller that just sent the features over PCIe does not want them
+        # back.  Only the fused prefix kernel has this mode.
+        self.edge_echo = bool(edge_echo)
         B, N, C, k, r = self.B, self.N, self.C, self.k, self.r
         s = r ** 3
         # The grid goes through L2 in chunks of clouds: voxelize(chunk) -> devoxelize(chunk) while the chunk's dense
@@ -72,21 +76,40 @@ class FrontEnd:
         self._chunks = [(b0, min(B, b0 + nb)) for b0 in range(0, B, nb)]
         f32, i32, dev = torch.float32, torch.int32, self.device
         with torch.cuda.device(dev):
-            # inputs
-            self.points = torch.zeros((B, 6, N), dtype=f32, device=dev)
-            self.features = torch.zeros((B, C, N), dtype=f32, device=dev)
+            # inputs and host-visible outputs live in ONE device buffer each, mirrored by one pinned host buffer each: the
+            # host-facing call moves them with a single copy per direction (five separate copies per step left ~10 % of the
+            # PCIe link idle between transfers)
+            ec = (2 if self.edge_echo else 1) * C
+
+            def carve(total_shapes, device=None, pinned=False):
+                offs, n = [], 0
+                for shp in total_shapes:
+                    offs.append(n)
+                    cnt = 1
+                    for d in shp:
+                        cnt *= d
+                    n += (cnt + 63) // 64 * 64                    # every view starts 256-byte aligned
+                buf = torch.zeros(max(n, 1), dtype=f32).pin_memory() if pinned else torch.zeros(max(n, 1), dtype=f32, device=device)
+                views = []
+                for shp, o in zip(total_shapes, offs):
+                    cnt = 1
+                    for d in shp:
+                        cnt *= d
+                    views.append(buf[o:o + cnt].view(shp))
+                return buf, views
+            in_shapes = [(B, 6, N), (B, C, N)]
+            out_shapes = [(B, 4, k, N), (B, C, N), (B, ec, N)]
+            self._in_pack, (self.points, self.features) = carve(in_shapes, device=dev)
+            self._out_pack, (self.ppf, self.devox, self.edge) = carve(out_shapes, device=dev)
             # branch A
             self.knn_dist = torch.empty((B, k, N), dtype=f32, device=dev)
             self.knn_idx = torch.empty((B, k, N), dtype=i32, device=dev)
-            self.ppf = torch.empty((B, 4, k, N), dtype=f32, device=dev)
             # branch B
             self.grid = torch.empty((B, C, r, r, r), dtype=f32, device=dev)
             self.ind = torch.empty((B, N), dtype=i32, device=dev)
             self.cnt = torch.empty((B, s), dtype=i32, device=dev)
-            self.devox = torch.empty((B, C, N), dtype=f32, device=dev)
             self.devox_inds = torch.empty((B, 8, N), dtype=i32, device=dev)
             self.devox_wgts = torch.empty((B, 8, N), dtype=f32, device=dev)
-            self.edge = torch.empty((B, 2 * C, N), dtype=f32, device=dev)
             self.xyz = torch.empty((B, 3, N), dtype=f32, device=dev)
             self.normals = torch.empty((B, 3, N), dtype=f32, device=dev)
             self._packed = torch.empty((B, N, 8), dtype=f32, device=dev)      # (x,y,z,nx,ny,nz,0,0) per point
@@ -100,13 +123,12 @@ class FrontEnd:
             self._main = torch.cuda.Stream(device=dev, priority=-1)
             self._devox_stream = torch.cuda.Stream(device=dev, priority=-1)
             # host staging (pinned)
-            self.h_points = torch.empty((B, 6, N), dtype=f32).pin_memory()
-            self.h_features = torch.empty((B, C, N), dtype=f32).pin_memory()
-            self.h_ppf = torch.empty((B, 4, k, N), dtype=f32).pin_memory()
-            self.h_devox = torch.empty((B, C, N), dtype=f32).pin_memory()
-            self.h_edge = torch.empty((B, 2 * C, N), dtype=f32).pin_memory()
+            self._h_in_pack, (self.h_points, self.h_features) = carve(in_shapes, pinned=True)
+            self._h_out_pack, (self.h_ppf, self.h_devox, self.h_edge) = carve(out_shapes, pinned=True)
         self._graph = None
         self._fused_front = self.grid_chunks == 1 and N <= 1024 and s % 4 == 0
+        if not self.edge_echo and not self._fused_front:
+            raise ValueError('edge_echo=False needs the fused prefix kernel (N <= 1024, r^3 % 4 == 0, one grid chunk)')
         # in-kernel mean (torch's reduction order, csrc/voxelize.cu): candidate only where that order is the one analysed
         # (128 <= N, N % 4 == 0); switched on by _verify_own_mean() at the first forward(), never silently
         self._own_mean = False
@@ -156,7 +178,7 @@ class FrontEnd:
         if fused:
             # prologue + prepare + means/edge in one launch, then the grid writer
             _check(_L.ri_vox_front_f32(self.points.data_ptr(), 6, mean.data_ptr(), self.features.data_ptr(), B, C, N, r,
-                                       shape, float(self.eps), self.NORM_MODE | (0x100 if own_mean else 0), self.norm_coords.data_ptr(),
+                                       shape, float(self.eps), self._front_mode(own_mean), self.norm_coords.data_ptr(),
                                        self._vox_coords.data_ptr(), self.ind.data_ptr(), self.edge.data_ptr(),
                                        self._ws.data_ptr(), self._ws_bytes, st), 'ri_vox_front')
             if fork is not None:
@@ -222,6 +244,10 @@ class FrontEnd:
         if self.devox_side_stream:
             main.wait_stream(self._devox_stream)
 
+    def _front_mode(self, own_mean):
+        """norm_mode argument of ri_vox_front_f32: radius association | in-kernel mean | relative-half-only edge output."""
+        return self.NORM_MODE | (0x100 if own_mean else 0) | (0 if self.edge_echo else 0x200)
+
     def _devox(self, b0, b1, st):
         """Devoxelize the clouds [b0, b1) of the batch (pointer offsets into the whole-batch arrays)."""
         N, C, r = self.N, self.C, self.r
@@ -270,7 +296,7 @@ class FrontEnd:
                 probe = torch.randn((B, 6, N), dtype=torch.float32, device=self.device, generator=g) * 3.0 + 0.7
                 probe[:, :3, ::stride] *= 1e3              # mixed magnitudes: any other summation order changes low bits
                 rc = _L.ri_vox_front_f32(probe.data_ptr(), 6, self._mean_buf.data_ptr(), self.features.data_ptr(), B, C, N, r,
-                                         shape, float(self.eps), self.NORM_MODE | 0x100, self.norm_coords.data_ptr(),
+                                         shape, float(self.eps), self._front_mode(True), self.norm_coords.data_ptr(),
                                          self._vox_coords.data_ptr(), self.ind.data_ptr(), self.edge.data_ptr(),
                                          self._ws.data_ptr(), self._ws_bytes, st)
                 if rc != 0:
@@ -322,14 +348,15 @@ class FrontEnd:
     def run_staged(self):
         """H2D from the pinned staging buffers -> step -> D2H into pinned buffers, then wait."""
         with torch.cuda.device(self.device):
-            self.points.copy_(self.h_points, non_blocking=True)
-            self.features.copy_(self.h_features, non_blocking=True)
+            self._in_pack.copy_(self._h_in_pack, non_blocking=True)
             self.forward()
-            self.h_ppf.copy_(self.ppf, non_blocking=True)
-            self.h_devox.copy_(self.devox, non_blocking=True)
-            self.h_edge.copy_(self.edge, non_blocking=True)
+            self._h_out_pack.copy_(self._out_pack, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-        return {'ppf': self.h_ppf, 'devox': self.h_devox, 'edge': self.h_edge}
+        return {'ppf': self.h_ppf, 'devox': self.h_devox, self._edge_key: self.h_edge}
+
+    @property
+    def _edge_key(self):
+        return 'edge' if self.edge_echo else 'edge_rel'
 
     # algorithmic (compulsory) bytes of one step, SURVEY.md §8(d) formulas, fused KNN->PPF form
     def algorithmic_bytes(self):
@@ -338,7 +365,7 @@ class FrontEnd:
         knn_ppf = 24 * N + 16 * k * N
         vox = 12 * N + 4 * C * N + 4 * N + 4 * s + 4 * C * s
         devox = 12 * N + 4 * N + min(32 * C * N, 4 * C * s) + 4 * C * N + 64 * N
-        edge = 4 * N + 4 * C * N + 4 * C * N + 8 * C * N
+        edge = 4 * N + 4 * C * N + 4 * C * N + (8 if self.edge_echo else 4) * C * N
         return {'knn_ppf': B * knn_ppf, 'voxelize': B * vox, 'devox': B * devox, 'edge': B * edge,
                 'total': B * (knn_ppf + vox + devox + edge)}
 
@@ -398,7 +425,7 @@ class FrontEndPipeline:
         s = pipe.acquire()                  # next slot, its previous results have been handed back
         pipe.slot(s).h_points[...] = ...    # fill the pinned inputs
         pipe.submit(s)                      # H2D -> step -> D2H, asynchronous
-        out = pipe.result(s)                # {'ppf', 'devox', 'edge'} pinned host tensors (waits for that slot only)
+        out = pipe.result(s)                # {'ppf', 'devox', 'edge' | 'edge_rel'} pinned host tensors (waits for that slot only)
     """
 
     def __init__(self, B, N, C, depth=3, device='cuda', **kw):
@@ -436,8 +463,7 @@ class FrontEndPipeline:
             # the slot's device inputs are free once its previous step has run; its device outputs once they were copied
             self._up.wait_event(self._ev_run[s])
             with torch.cuda.stream(self._up):
-                fe.points.copy_(fe.h_points, non_blocking=True)
-                fe.features.copy_(fe.h_features, non_blocking=True)
+                fe._in_pack.copy_(fe._h_in_pack, non_blocking=True)
                 self._ev_up[s].record(self._up)
             self._run.wait_event(self._ev_up[s])
             self._run.wait_event(self._ev_down[s])
@@ -446,9 +472,7 @@ class FrontEndPipeline:
                 self._ev_run[s].record(self._run)
             self._down.wait_event(self._ev_run[s])
             with torch.cuda.stream(self._down):
-                fe.h_ppf.copy_(fe.ppf, non_blocking=True)
-                fe.h_devox.copy_(fe.devox, non_blocking=True)
-                fe.h_edge.copy_(fe.edge, non_blocking=True)
+                fe._h_out_pack.copy_(fe._out_pack, non_blocking=True)
                 self._ev_down[s].record(self._down)
         self._busy[s] = True
 
@@ -456,7 +480,7 @@ class FrontEndPipeline:
         self._ev_down[s].synchronize()
         self._busy[s] = False
         fe = self.slots[s]
-        return {'ppf': fe.h_ppf, 'devox': fe.h_devox, 'edge': fe.h_edge}
+        return {'ppf': fe.h_ppf, 'devox': fe.h_devox, fe._edge_key: fe.h_edge}
 
     def drain(self):
         for s in range(self.depth):

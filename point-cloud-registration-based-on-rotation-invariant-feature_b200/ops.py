@@ -412,7 +412,9 @@ def _(avg, features, inds):
 @torch.library.custom_op("ri::knn_ppf", mutates_args=())
 def knn_ppf(xyz: torch.Tensor, normals: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Self-query k-NN and the PPF of every (point, neighbour) pair: xyz, normals [B,3,N] -> dist [B,k,N], idx [B,k,N],
-    ppf [B,4,k,N].  One fused kernel while N <= 2048 and k <= 32, the k-NN + gather/PPF pair otherwise (same values)."""
+    ppf [B,4,k,N].  Up to 1024 points: the warp-per-query k-NN followed by the gather/PPF kernel (39 + 16 us at 32 x 1024,
+    k = 20, against 127 us for the fused thread-per-query kernel); up to 2048 points and k <= 32: the fused kernel
+    (ri_knn_ppf_f32); larger: the hash-grid k-NN + gather/PPF.  Same values on every path."""
     _req(xyz, "xyz", torch.float32); _req(normals, "normals", torch.float32)
     dev = _same_device(xyz, normals)
     B, c, N = xyz.shape
@@ -422,7 +424,7 @@ def knn_ppf(xyz: torch.Tensor, normals: torch.Tensor, k: int) -> tuple[torch.Ten
         d = torch.empty((B, k, N), dtype=torch.float32, device=dev)
         i = torch.empty((B, k, N), dtype=torch.int32, device=dev)
         out = torch.empty((B, 4, k, N), dtype=torch.float32, device=dev)
-        if N <= 2048 and k <= 32:
+        if 1024 < N <= 2048 and k <= 32:
             _check(_L.ri_knn_ppf_f32(xyz.data_ptr(), normals.data_ptr(), 3 * N, B, N, k, d.data_ptr(), i.data_ptr(),
                                      out.data_ptr(), _stream()), "ri_knn_ppf")
         else:

@@ -8,7 +8,7 @@ import os
 import torch
 import torch.distributed as dist
 
-__all__ = ['init_from_env', 'shard_range', 'gather_clouds', 'max_over_ranks']
+__all__ = ['init_from_env', 'shard_range', 'gather_clouds', 'max_over_ranks', 'bind_host_to_gpu']
 
 
 def init_from_env(backend=None):
@@ -58,3 +58,44 @@ def max_over_ranks(value, device):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(index):
+    """Host side of a rank that feeds GPU `index` over PCIe: restrict the process to the CPU cores of the NUMA node the GPU
+    hangs off and prefer that node for new pages, BEFORE any pinned buffer is allocated — eight ranks that stage through
+    the memory of one socket share its controllers and cross the socket link for half of the GPUs.  Returns
+    {'node', 'cpus', 'mempolicy'} or None when the topology cannot be read (containers without /sys, single-node hosts)."""
+    try:
+        props = torch.cuda.get_device_properties(index)
+        bus = '%04x:%02x:%02x.0' % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read())
+        if node < 0:
+            return None
+        cpus = _parse_cpulist(open('/sys/devices/system/node/node%d/cpulist' % node).read())
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        policy = False
+        try:                                            # set_mempolicy(MPOL_PREFERRED, {node}): syscall 238 on x86-64
+            import ctypes
+            import platform
+            if platform.machine() == 'x86_64' and node < 64:
+                libc = ctypes.CDLL(None, use_errno=True)
+                mask = ctypes.c_ulong(1 << node)
+                policy = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(65)) == 0
+        except Exception:
+            policy = False
+        return {'node': node, 'cpus': len(cpus), 'mempolicy': bool(policy)}
+    except Exception:
+        return None

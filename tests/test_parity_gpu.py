@@ -107,6 +107,12 @@ def test_knn_ppf_fused_equals_two_kernels(ri):
         p0 = torch.ops.ri.ppf_gather(xyz, nrm, i0)
         d1, i1, p1 = torch.ops.ri.knn_ppf(xyz, nrm, k)
         assert torch.equal(i0, i1) and torch.equal(d0, d1) and torch.equal(p0, p1)
+        if N <= 2048 and k <= 32:                                       # the fused kernel itself, whatever the op dispatches to
+            L = ri._lib
+            d2 = torch.empty_like(d0); i2 = torch.empty_like(i0); p2 = torch.empty_like(p0)
+            L.check(L.lib.ri_knn_ppf_f32(xyz.data_ptr(), nrm.data_ptr(), 3 * N, B, N, k, d2.data_ptr(), i2.data_ptr(),
+                                         p2.data_ptr(), torch.cuda.current_stream().cuda_stream), "knn_ppf")
+            assert torch.equal(i0, i2) and torch.equal(d0, d2) and torch.equal(p0, p2)
     # straight off the interleaved [B,6,N] batch (cloud stride 6N), as the front-end engine calls it
     pts = T(clouds(4, 1024, 5)); B, N, k = 4, 1024, 20
     L = ri._lib
