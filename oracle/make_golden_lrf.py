@@ -2,9 +2,8 @@
 
 The reference code for this path is pure torch inside PVCNN_classifier.forward (PVCNN/models/pvcnn_classify.py:153-184);
 the class cannot be instantiated here (its other branches need open3d and the CUDA backend), so the fixture is produced by
-running THOSE LINES' torch operations, in their order, on the CPU: same calls (`mean`, `norm(dim=1)`, `argsort(descending)`,
-`.norm()`, `(a*b).sum()`, `bmm`, `cross`), same loops, same thresholds.  Pin strength: a transcription, not the imported
-class — stated as such in DESIGN.md.
+EXECUTING those statements: oracle/ref_extract.py cuts the `change_coords` branch out of the reference file by its syntax
+tree, wraps it in a function of (coords, b, n) and runs it on the CPU.  Pin strength: reference-executed.
 
     python oracle/make_golden_lrf.py        # writes tests/golden/lrf.npz
 """
@@ -19,37 +18,13 @@ sys.path.insert(0, ROOT)
 
 
 def change_coords_torch(coords):
-    """The torch calls of pvcnn_classify.py:153-184 in their order (mean, norm(dim=1), argsort(descending), per-vector norm(),
-    (a*b).sum(), bmm, cross, norm(dim=1)) — written out here, not imported: see the module docstring."""
-    nb, _, npts = coords.shape
-    centred = coords - coords.mean(dim=2, keepdim=True)                                   # :154
-    by_radius = torch.argsort(centred.norm(dim=1), dim=1, descending=True)                # :155
-    ex = torch.zeros(nb, 3, 1).to(centred)
-    ey = torch.zeros(nb, 3, 1).to(centred)
-    for c in range(nb):
-        first = centred[c, :, by_radius[c, 0]]                                            # :159
-        assert first.norm() > 1e-5                                                        # :160
-        first = first / first.norm()
-        second, cosang = None, None
-        for q in range(1, npts):                                                          # :162-169
-            cand = centred[c, :, by_radius[c, q]]
-            if cand.norm() < 1e-5:
-                continue
-            cand = cand / cand.norm()
-            cosang = (first * cand).sum()
-            if cosang < 0.9 and cosang > -0.9:
-                second = cand
-                break
-        assert second is not None                                                         # :170
-        ex[c, :, :] = first.unsqueeze(1)
-        ey[c, :, :] = second.unsqueeze(1)
-    ex -= ey * (ex.permute(0, 2, 1).bmm(ey))                                              # :175 Gram-Schmidt, y kept
-    assert (ex.norm(dim=1, keepdim=True) < 1e-5).sum() < 1                                # :176
-    ex /= ex.norm(dim=1, keepdim=True)                                                    # :177
-    ez = ex.cross(ey, dim=1)                                                              # :179
-    ez = ez / ez.norm(dim=1, keepdim=True)                                                # :180
-    rows = [axis.permute(0, 2, 1).bmm(centred) for axis in (ex, ey, ez)]                  # :181-183
-    return torch.cat(rows, dim=1), torch.cat((ex, ey, ez), dim=2).permute(0, 2, 1)
+    """The reference branch itself: its statements are cut out of pvcnn_classify.py by their syntax tree
+    (oracle/ref_extract.py) and executed on `coords` — nothing of it is retyped here."""
+    from oracle import ref_extract
+    f, lines = ref_extract.change_coords_function()
+    features, ex, ey, ez = f(coords)
+    change_coords_torch.lines = lines
+    return features, torch.cat((ex, ey, ez), dim=2).permute(0, 2, 1)
 
 
 def main():
@@ -72,6 +47,7 @@ def main():
         out[name + "_mean"] = t.mean(dim=2).numpy()
         out[name + "_new"] = new.numpy()
         out[name + "_bases"] = bases.contiguous().numpy()
+    out["reference_lines"] = np.array(change_coords_torch.lines)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "lrf.npz"), **out)
     print({k: v.shape for k, v in out.items()})
 
