@@ -64,6 +64,7 @@ for _r in (16, 64):
                                      name="sph_dg front end at spherical res %d: 32 x 1024 pts per step, k=20 KNN+PPF, C=67 "
                                           "(BASELINE configs[4] sweep)" % _r)
 RING = 3            # independent input/output buffer sets cycled between timed steps (footprint > L2)
+LANES = 2           # steps in flight (tools/tune_lanes.py: cu_dg 140 / 149 / 149 us per step with 2 / 3 / 4 in flight, sph_dg 121 throughout)
 MIN_TIMED_MS = 250  # every timed region lasts at least this long
 E2E_DEPTH = 4       # slots of the host-facing pipeline (tools/exp_e2e.py: 2 / 3 / 4 / 6 slots -> 0.578 / 0.579 / 0.547 / 0.552 ms per step)
 
@@ -218,7 +219,7 @@ def measure_workload(key, args, ri_b200, H, rank, world, local, headline):
     #      stream, so the latency-bound prefix and the k-NN of one batch run under the grid write / devoxelize of
     #      another); every step is launched after the start event and has finished before the end event.  At N > 1 each
     #      step's voxel indices ([B,N] int32) are all-gathered over NCCL behind the step: the result gather.
-    lanes = ri_b200.FrontEndLanes(engines, lanes=RING)
+    lanes = ri_b200.FrontEndLanes(engines, lanes=LANES)
     gathered = [torch.empty((world * B, N), dtype=torch.int32, device=dev) for _ in range(RING)] if world > 1 else None
     gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
 
@@ -445,9 +446,9 @@ def run_ours(args, rank, world, local):
         "ms_per_step": head["ms_per_step"], "timed_steps": head["timed_steps"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_for(wl, world),
-        "notes": {"cuda_graph": True, "steps_in_flight": RING, "grid_chunks": meta["grid_chunks"],
+        "notes": {"cuda_graph": True, "steps_in_flight": LANES, "grid_chunks": meta["grid_chunks"],
                   "overlap": "k-NN/PPF branch on a side stream next to the grid writer and the devoxelizer; %d independent "
-                             "batches in flight on %d launch streams" % (RING, RING),
+                             "batches in flight on %d launch streams, %d buffer sets cycled" % (LANES, LANES, RING),
                   "one_step_at_a_time": head["one_step_at_a_time"],
                   "result_gather": ("all_gather_into_tensor of every step's voxel indices [B,N] i32 over NCCL, inside the timed region"
                                     if world > 1 else "single GPU: nothing to gather"),

@@ -127,6 +127,9 @@ devox_kernel(const float* __restrict__ coords, const float* __restrict__ feat, c
 constexpr int kSdThreads = 256;                     // consumer threads
 constexpr int kSdWarps = kSdThreads / 32;
 constexpr int kSdMaxRing = 8;
+// registers: min-CTAs 2 caps the kernel at 112 registers per thread (288 threads: 32 K of the SM's 64 K), so that a CTA of
+// the voxel branch's prefix kernel (512 threads x 64 registers) of ANOTHER batch in flight fits on the SM next to it
+constexpr int kSdMinCtas = 2;
 constexpr uint32_t kSdTileBytesDefault = 64u << 10;   // measured: 8 / 16 / 32 / 64 KB tiles -> 154 / 91 / 58 / 56 us (B200, 32 x 71 planes)
 constexpr uint32_t kSdRingBytesDefault = 128u << 10;   // leaves room for k-NN CTAs on the same SM
 
@@ -161,7 +164,7 @@ __device__ __forceinline__ void sd_bulk_g2s(uint32_t dst, const void* src, uint3
 }
 
 template <int P>
-__global__ void __launch_bounds__(kSdThreads + 32, 1)
+__global__ void __launch_bounds__(kSdThreads + 32, kSdMinCtas)
 devox_stream_kernel(const float* __restrict__ coords, const float* __restrict__ feat, int B, int C, int N, int r,
                     int TS, int nt, uint32_t slot_bytes, int R,
                     float* __restrict__ outs, int* __restrict__ inds, float* __restrict__ wgts, int dbg_skip)
@@ -311,15 +314,15 @@ static bool sd_plan(const float* feat, int C, int N, int r, SdPlan& pl)
 {
     // RI_DEVOX_STREAM=0 forces the gather form, =1 takes the streaming form wherever it is able to run (tests compare
     // the two); unset: streaming where a whole plane is not much more than what the gathers would move
-    const char* ev = getenv("RI_DEVOX_STREAM");
-    const int mode = ev ? atoi(ev) + 1 : 0;
+    const RiEnv& env = ri_env();
+    const int mode = env.devox_stream >= 0 ? env.devox_stream + 1 : 0;
     if (mode == 1) return false;
     if (C < 1 || N < 1 || N > kSdThreads * 8 || (r & 1) || r < 2) return false;
     if (((uintptr_t)feat & 15) != 0) return false;
     const size_t slab = (size_t)r * r * 4, plane = slab * r;
     uint32_t tile_bytes = kSdTileBytesDefault, ring_bytes = kSdRingBytesDefault;
-    if (const char* e2 = getenv("RI_DEVOX_TILE_KB")) { const int v = atoi(e2); if (v >= 1 && v <= 96) tile_bytes = (uint32_t)v << 10; }
-    if (const char* e3 = getenv("RI_DEVOX_RING_KB")) { const int v = atoi(e3); if (v >= 2 && v <= 208) ring_bytes = (uint32_t)v << 10; }
+    if (env.devox_tile_kb >= 1 && env.devox_tile_kb <= 96) tile_bytes = (uint32_t)env.devox_tile_kb << 10;
+    if (env.devox_ring_kb >= 2 && env.devox_ring_kb <= 208) ring_bytes = (uint32_t)env.devox_ring_kb << 10;
     if (slab > tile_bytes) return false;
     if (plane / 4 >= (1u << 28)) return false;      // base index is packed into 28 bits
     // the gather form moves ~128 B per point and plane; stream only where a whole plane is not much more than that
@@ -341,14 +344,13 @@ static int sd_launch(const SdPlan& pl, const float* coords, const float* feat, i
 {
     auto kern = devox_stream_kernel<P>;
     size_t smem = (size_t)pl.R * pl.slot_bytes;
-    if (const char* ev = getenv("RI_DEVOX_PAD_KB")) { const int v = atoi(ev); if (v >= 0 && v <= 64) smem += (size_t)v << 10; }
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    ri_prefer_step_carveout(kern);
+    const RiEnv& env = ri_env();
+    if (env.devox_pad_kb >= 0 && env.devox_pad_kb <= 64) smem += (size_t)env.devox_pad_kb << 10;
+    RI_KERNEL_SETUP(kern, true, ri_step_carveout_percent());
     const long long planes = (long long)B * C;
     const int grid = planes < ri_num_sms() ? (int)planes : ri_num_sms();
     kern<<<grid, kSdThreads + 32, smem, st>>>(coords, feat, B, C, N, r, pl.TS, pl.nt, pl.slot_bytes, pl.R, outs, inds, wgts,
-                                              getenv("RI_DEVOX_DBG_SKIP") != nullptr ? 1 : 0);
+                                              env.devox_dbg_skip);
     RI_LAUNCH_CHECK();
     return RI_OK;
 }

@@ -229,17 +229,10 @@ int launch_knn(const float* queries, const float* refs, int B, int c, int n, int
         return ri_launch_knn_warp(queries, refs, B, n, m, k, dist, idx, st);      // knn_warp.cu: a warp per query
     dim3 grid((n + kQueriesPerCta - 1) / kQueriesPerCta, B);
     const size_t smem = (size_t)(m < kRefTile ? (m > 0 ? m : 1) : kRefTile) * sizeof(float4);
-    static bool carveout_set = false;
-    if (!carveout_set) {
-        ri_prefer_step_carveout(knn3_kernel<8>); ri_prefer_step_carveout(knn3_kernel<16>);
-        ri_prefer_step_carveout(knn3_kernel<20>); ri_prefer_step_carveout(knn3_kernel<32>);
-        carveout_set = true;
-    }
     if (c == 3 && k <= 32) {
-        if (k <= 8) knn3_kernel<8><<<grid, kQueriesPerCta, smem, st>>>(queries, refs, n, m, k, dist, idx);
-        else if (k <= 16) knn3_kernel<16><<<grid, kQueriesPerCta, smem, st>>>(queries, refs, n, m, k, dist, idx);
-        else if (k <= 20) knn3_kernel<20><<<grid, kQueriesPerCta, smem, st>>>(queries, refs, n, m, k, dist, idx);
-        else knn3_kernel<32><<<grid, kQueriesPerCta, smem, st>>>(queries, refs, n, m, k, dist, idx);
+        auto kern = k <= 8 ? knn3_kernel<8> : k <= 16 ? knn3_kernel<16> : k <= 20 ? knn3_kernel<20> : knn3_kernel<32>;
+        RI_KERNEL_SETUP(kern, false, ri_step_carveout_percent());
+        kern<<<grid, kQueriesPerCta, smem, st>>>(queries, refs, n, m, k, dist, idx);
     } else {
         knn_generic_kernel<<<grid, kQueriesPerCta, 0, st>>>(queries, refs, c, n, m, k, dist, idx);
     }
@@ -288,21 +281,10 @@ extern "C" int ri_knn_ppf_f32(const float* xyz, const float* normals, long long 
     if (B == 0 || N == 0) return RI_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)N * 2 * sizeof(float4);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(knn3_ppf_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kRefTile * sizeof(float4)));
-        cudaFuncSetAttribute(knn3_ppf_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kRefTile * sizeof(float4)));
-        cudaFuncSetAttribute(knn3_ppf_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kRefTile * sizeof(float4)));
-        cudaFuncSetAttribute(knn3_ppf_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kRefTile * sizeof(float4)));
-        ri_prefer_step_carveout(knn3_ppf_kernel<8>); ri_prefer_step_carveout(knn3_ppf_kernel<16>);
-        ri_prefer_step_carveout(knn3_ppf_kernel<20>); ri_prefer_step_carveout(knn3_ppf_kernel<32>);
-        attr_set = true;
-    }
     dim3 grid((N + kQueriesPerCta - 1) / kQueriesPerCta, B);
-    if (k <= 8) knn3_ppf_kernel<8><<<grid, kQueriesPerCta, smem, st>>>(xyz, normals, cloud_stride, N, k, dist, idx, ppf);
-    else if (k <= 16) knn3_ppf_kernel<16><<<grid, kQueriesPerCta, smem, st>>>(xyz, normals, cloud_stride, N, k, dist, idx, ppf);
-    else if (k <= 20) knn3_ppf_kernel<20><<<grid, kQueriesPerCta, smem, st>>>(xyz, normals, cloud_stride, N, k, dist, idx, ppf);
-    else knn3_ppf_kernel<32><<<grid, kQueriesPerCta, smem, st>>>(xyz, normals, cloud_stride, N, k, dist, idx, ppf);
+    auto kern = k <= 8 ? knn3_ppf_kernel<8> : k <= 16 ? knn3_ppf_kernel<16> : k <= 20 ? knn3_ppf_kernel<20> : knn3_ppf_kernel<32>;
+    RI_KERNEL_SETUP(kern, true, ri_step_carveout_percent());        // up to 64 KB of dynamic shared memory: per-device opt-in
+    kern<<<grid, kQueriesPerCta, smem, st>>>(xyz, normals, cloud_stride, N, k, dist, idx, ppf);
     RI_LAUNCH_CHECK();
     return RI_OK;
 }

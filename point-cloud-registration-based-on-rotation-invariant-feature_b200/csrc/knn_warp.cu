@@ -270,7 +270,7 @@ int launch_nb(const float* queries, const float* refs, int B, int n, int m, int 
     warps = (total + qpw - 1) / qpw;
     const int ctas = (int)((warps + kWarpsPerCta - 1) / kWarpsPerCta);
     const size_t smem = (size_t)kWarpsPerCta * WarpSmem<NB>::kWords * sizeof(unsigned long long);
-    cudaFuncSetAttribute(knn3_warp_kernel<NB>, cudaFuncAttributePreferredSharedMemoryCarveout, ri_step_carveout_percent());
+    RI_KERNEL_SETUP(knn3_warp_kernel<NB>, false, ri_step_carveout_percent());
     knn3_warp_kernel<NB><<<ctas, 32 * kWarpsPerCta, smem, st>>>(queries, refs, n, m, k, total, (int)qpw, dist, idx);
     RI_LAUNCH_CHECK();
     return RI_OK;

@@ -139,18 +139,11 @@ extern "C" int ri_ppf_gather_f32(const float* xyz, const float* normals, const i
     dim3 grid((N + centres - 1) / centres, B);
     const size_t smem = (size_t)N * 2 * sizeof(float4);
     cudaStream_t st = (cudaStream_t)stream;
-    static bool carveout_set = false;
-    if (!carveout_set) {
-        ri_prefer_step_carveout(ppf_gather_kernel<true>); ri_prefer_step_carveout(ppf_gather_kernel<false>);
-        carveout_set = true;
-    }
     if (smem <= 160 * 1024) {
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(ppf_gather_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-        }
+        RI_KERNEL_SETUP(ppf_gather_kernel<true>, true, ri_step_carveout_percent());
         ppf_gather_kernel<true><<<grid, kGatherThreads, smem, st>>>(xyz, normals, idx, N, k, centres, out);
     } else {
+        RI_KERNEL_SETUP(ppf_gather_kernel<false>, false, ri_step_carveout_percent());
         ppf_gather_kernel<false><<<grid, kGatherThreads, 0, st>>>(xyz, normals, idx, N, k, centres, out);
     }
     RI_LAUNCH_CHECK();
@@ -168,12 +161,7 @@ extern "C" int ri_ppf_gather_packed_f32(const float* packed, const int* idx, int
     dim3 grid((unsigned)((kN + kGatherThreads - 1) / kGatherThreads), B);
     // no shared memory, but the carveout PREFERENCE still decides which kernels an SM can host at the same time: ask for
     // the step's split so it runs next to the streaming devoxelizer / grid writer / k-NN (RI_PPF_MAXL1=1: the default split)
-    static int carveout_set = 0;
-    if (!carveout_set) {
-        const char* ev = getenv("RI_PPF_MAXL1");
-        if (!(ev && atoi(ev) == 1)) ri_prefer_step_carveout(ppf_gather_packed_kernel);
-        carveout_set = 1;
-    }
+    if (!ri_env().ppf_maxl1) RI_KERNEL_SETUP(ppf_gather_packed_kernel, false, ri_step_carveout_percent());
     ppf_gather_packed_kernel<<<grid, kGatherThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(packed), idx, N, k, out);
     RI_LAUNCH_CHECK();
     return RI_OK;

@@ -77,8 +77,7 @@ extern "C" int ri_vox_prologue_f32(const float* points, int pstride, const float
     if (B < 0 || N < 0 || r <= 0 || (pstride != 3 && pstride != 6) || shape < 0 || shape > 2) return RI_ERR_BAD_ARG;
     if (norm_coords == nullptr || (shape != 2 && vox_coords == nullptr)) return RI_ERR_BAD_ARG;
     if (B == 0 || N == 0) return RI_OK;
-    static bool carveout_set = false;
-    if (!carveout_set) { ri_prefer_step_carveout(prologue_kernel); carveout_set = true; }
+    RI_KERNEL_SETUP(prologue_kernel, false, ri_step_carveout_percent());
     prologue_kernel<<<B, kProThreads, 0, (cudaStream_t)stream>>>(points, pstride, mean, N, r, shape, eps, norm_mode,
                                                                  xyz, normals, norm_coords, vox_coords);
     RI_LAUNCH_CHECK();
@@ -121,8 +120,7 @@ extern "C" int ri_split_xyz_normals_f32(const float* points, int B, int N, float
 {
     if (B < 0 || N < 0 || B > 65535 || ((uintptr_t)packed & 15) != 0) return RI_ERR_BAD_ARG;
     if (B == 0 || N == 0) return RI_OK;
-    static bool carveout_set = false;
-    if (!carveout_set) { ri_prefer_step_carveout(split6_kernel); carveout_set = true; }
+    RI_KERNEL_SETUP(split6_kernel, false, ri_step_carveout_percent());
     dim3 grid((unsigned)((N + 255) / 256 > 16 ? 16 : (N + 255) / 256), B);
     split6_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(points, N, xyz, normals, reinterpret_cast<float4*>(packed));
     RI_LAUNCH_CHECK();

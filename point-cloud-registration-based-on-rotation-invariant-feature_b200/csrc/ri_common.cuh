@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <atomic>
 
 #define RI_OK 0
 #define RI_ERR_BAD_ARG (-1)
@@ -27,40 +28,135 @@
         if (e__ != cudaSuccess) return (int)e__;            \
     } while (0)
 
+// ---- process-wide state of the library: everything below is read-only after its first use and safe to reach from several
+// host threads and several devices of one process (the reference trains with single-process nn.DataParallel) -----------
+
+// Environment knobs (experiments and tests — none changes a result).  Read ONCE per process: the
+// initialisation of a function-local static is thread-safe, the launch paths never call getenv().
+struct RiEnv {
+    int carveout_pct;                       // RI_CARVEOUT_PCT       shared-memory carveout preference of the step's kernels
+    int devox_stream;                       // RI_DEVOX_STREAM       -1 unset, 0 gather form, 1 streaming form wherever it can run
+    int devox_tile_kb, devox_ring_kb, devox_pad_kb, devox_dbg_skip;
+    int fill_ring, fill_ctas, fill_pad_kb;  // RI_FILL_*             grid writer: slots per warp, CTAs per SM, shared-memory padding
+    int fill_group;                         // RI_FILL_GROUP         grid writer: planes per work item
+    int fill_warps, fill_listcap, fill_tile_cells;   // RI_FILL_WARPS / _LISTCAP / _TILE   writer warps per CTA, staged cells per tile, cells per tile
+    int vox_atomic;                         // RI_VOX_ATOMIC         scan-sized clouds: memset + float atomics
+    int ppf_maxl1;                          // RI_PPF_MAXL1          packed PPF kernel keeps the default (max-L1) split
+    int match_pair;                         // RI_MATCH_PAIR         -1 unset, 0 single-CTA form, 1 CTA-pair form
+    int match_dbg;                          // RI_MATCH_DBG          GEMM only, %globaltimer stamps in the workspace
+    int fill_form;                          // RI_FILL_FORM          -1 unset, 0 CTA-synchronous writer, 1 warp-autonomous writer
+};
+static inline int ri_env_int(const char* name, int unset)
+{
+    const char* ev = getenv(name);
+    return ev ? atoi(ev) : unset;
+}
+static inline const RiEnv& ri_env()
+{
+    static const RiEnv env = [] {
+        RiEnv e;
+        e.carveout_pct = ri_env_int("RI_CARVEOUT_PCT", 100);
+        if (e.carveout_pct < 1 || e.carveout_pct > 100) e.carveout_pct = 100;
+        e.devox_stream = ri_env_int("RI_DEVOX_STREAM", -1);
+        e.devox_tile_kb = ri_env_int("RI_DEVOX_TILE_KB", -1);
+        e.devox_ring_kb = ri_env_int("RI_DEVOX_RING_KB", -1);
+        e.devox_pad_kb = ri_env_int("RI_DEVOX_PAD_KB", -1);
+        e.devox_dbg_skip = getenv("RI_DEVOX_DBG_SKIP") != nullptr;
+        e.fill_ring = ri_env_int("RI_FILL_RING", -1);
+        e.fill_ctas = ri_env_int("RI_FILL_CTAS", -1);
+        e.fill_pad_kb = ri_env_int("RI_FILL_PAD_KB", -1);
+        e.fill_group = ri_env_int("RI_FILL_GROUP", -1);
+        e.fill_warps = ri_env_int("RI_FILL_WARPS", -1);
+        e.fill_listcap = ri_env_int("RI_FILL_LISTCAP", -1);
+        e.fill_tile_cells = ri_env_int("RI_FILL_TILE", -1);
+        e.vox_atomic = getenv("RI_VOX_ATOMIC") != nullptr;
+        e.ppf_maxl1 = ri_env_int("RI_PPF_MAXL1", 0) == 1;
+        e.match_pair = ri_env_int("RI_MATCH_PAIR", -1);
+        e.match_dbg = getenv("RI_MATCH_DBG") != nullptr;
+        e.fill_form = ri_env_int("RI_FILL_FORM", -1);
+        return e;
+    }();
+    return env;
+}
+
+// SM count of the CURRENT device, cached per device ordinal.
 static inline int ri_num_sms()
 {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = RI_SM_COUNT_FALLBACK;
-        cached = n;
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return RI_SM_COUNT_FALLBACK;
+    const int slot = dev & 63;
+    int n = cached[slot].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = RI_SM_COUNT_FALLBACK;
+        cached[slot].store(n, std::memory_order_relaxed);
     }
-    return cached;
+    return n;
 }
 
 // L1 / shared-memory split of the kernels that are meant to run NEXT TO the grid writer (vox_fill: a 96 KB ring per SM).
 // An SM cannot host CTAs of kernels configured for different carveouts at the same time — it drains first — which
 // silently serialises branches that were meant to overlap (measured on a B200: k-NN next to the grid writer 154 us with
 // mismatched carveouts, 108 us matched; k-NN next to the devoxelizer 285 us against 78 + 54 us one after the other).
-// So the k-NN / PPF branch and the prefix of the voxel branch all ask for the writer's max-shared split.  The
+// So the k-NN / PPF branch and the prefix of the voxel branch all ask for the writer's max-shared split.  The gather
 // devoxelizer must NOT: its gathers use L1 as their miss buffer and its speed follows the L1 size (54 us with the
 // default max-L1 split, 73 / 88 / 118 / 231 us with 100 / 132 / 164 / 228 KB of shared memory), so it keeps the default
 // and is scheduled after the max-shared kernels have left the SMs.
-static inline int ri_step_carveout_percent()
+static inline int ri_step_carveout_percent() { return ri_env().carveout_pct; }
+
+// Function attributes are PER DEVICE (and a kernel's dynamic shared memory above 48 KB is an opt-in): they are set the
+// first time a kernel is launched on a device, not once per process and not on every launch.  One lock-free table per
+// translation unit, keyed by the kernel's address: slot = {kernel, bit mask of the devices done}.  Two threads racing on
+// the same (kernel, device) both set the same values — harmless.
+//   smem_optin  raise cudaFuncAttributeMaxDynamicSharedMemorySize to everything the device allows (minus the kernel's
+//               static shared memory), so any later launch size is legal
+//   carveout    >= 0: cudaFuncAttributePreferredSharedMemoryCarveout
+static inline cudaError_t ri_kernel_setup(const void* kernel, bool smem_optin, int carveout)
 {
-    static int pct = 0;
-    if (pct == 0) {
-        pct = 100;
-        if (const char* ev = getenv("RI_CARVEOUT_PCT")) { const int v = atoi(ev); if (v >= 1 && v <= 100) pct = v; }
+    constexpr int kSlots = 128;
+    static std::atomic<const void*> key[kSlots];
+    static std::atomic<unsigned long long> done[kSlots];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    int slot = (int)(((uintptr_t)kernel >> 4) % kSlots);
+    for (int probe = 0; probe < kSlots; ++probe, slot = (slot + 1) % kSlots) {
+        const void* cur = key[slot].load(std::memory_order_acquire);
+        if (cur == kernel) break;
+        if (cur == nullptr) {
+            const void* expected = nullptr;
+            if (key[slot].compare_exchange_strong(expected, kernel, std::memory_order_acq_rel) || expected == kernel) break;
+        }
     }
-    return pct;
+    const bool tracked = key[slot].load(std::memory_order_acquire) == kernel;       // table full: set on every launch
+    if (tracked && (done[slot].load(std::memory_order_acquire) & bit)) return cudaSuccess;
+    if (smem_optin) {
+        int optin = 0;
+        cudaFuncAttributes fa;
+        e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncGetAttributes(&fa, kernel);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+        if (e != cudaSuccess) return e;
+    }
+    if (carveout >= 0) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+        if (e != cudaSuccess) return e;
+    }
+    if (tracked) done[slot].fetch_or(bit, std::memory_order_release);
+    return cudaSuccess;
 }
+#define RI_KERNEL_SETUP(kernel, smem_optin, carveout)                                              \
+    do {                                                                                           \
+        cudaError_t e__ = ri_kernel_setup((const void*)(kernel), (smem_optin), (carveout));        \
+        if (e__ != cudaSuccess) return (int)e__;                                                   \
+    } while (0)
 template <typename K>
 static inline void ri_prefer_step_carveout(K kernel)
 {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, ri_step_carveout_percent());
+    ri_kernel_setup((const void*)kernel, false, ri_step_carveout_percent());
 }
 
 // x*x' + y*y' + z*z' as nvcc contracts it for the reference: fma(z,z', fma(x,x', y*y')).

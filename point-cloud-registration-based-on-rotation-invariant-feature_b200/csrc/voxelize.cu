@@ -43,15 +43,15 @@ namespace {
 
 constexpr int kPrepThreads = 512;
 constexpr int kSmallCloudMax = 4096;     // K1 sorts a whole cloud inside one CTA
-constexpr int kTileCells = 8192;         // 32 KB of fp32 per tile
-constexpr int kRing = 3;                 // default number of 32 KB tiles in a CTA's ring
-constexpr int kFillThreads = 256;
-constexpr int kFillCtasPerSm = 1;         // one 96 KB ring per SM keeps the bulk-store engine fed (measured: same speed as two)
+constexpr int kTileCells = 2048;         // 8 KB of fp32 per grid tile: one bulk store
+constexpr int kFwWarps = 4;              // autonomous writer warps per CTA (grid writer), one CTA per SM (see the launch)
+constexpr int kFwMaxWarps = 8;
+constexpr int kFwSlots = 2;              // 8 KB tiles in a warp's ring
+constexpr int kFillCtasPerSm = 1;
 constexpr int kMaxFillCalls = 64;        // distinct cloud ranges one workspace can serve between two prepares
 constexpr int kPlaneBatch = 4;            // channel planes whose table reads are issued together
-constexpr int kPlaneGroup = 8;            // planes per work item (>= kRing)
-constexpr int kFillMaxRegs = 80;          // a small footprint: the k-NN / PPF CTAs of the other branch share the SM
-constexpr int kSegCache = 2;             // occupied cells per thread whose table entries live in registers
+constexpr int kPlaneGroup = 8;            // planes per work item (>= kFwSlots)
+constexpr int kListCapDefault = 768;     // occupied cells of a tile whose ids / values a writer warp stages in shared memory
 constexpr unsigned kNoCell = 0xffffffffu;
 
 struct VoxWs {                            // per-cloud int32 workspace layout
@@ -75,9 +75,10 @@ __host__ __device__ inline VoxWs vox_ws_layout(int N, int ntiles)
 template <bool SPH>
 __global__ void __launch_bounds__(kPrepThreads)
 vox_prepare_kernel(const void* __restrict__ coords_v, int N, int P, int r, int s, int tile_cells, int ntiles,
-                   int* __restrict__ ind, int* __restrict__ ws)
+                   int* __restrict__ ind, int* __restrict__ ws, int* __restrict__ fill_counters)
 {
     extern __shared__ unsigned long long skeys[];          // [P] keys, then [P] ints of segment cells
+    if (blockIdx.x == 0 && threadIdx.x < 2 * kMaxFillCalls) fill_counters[threadIdx.x] = 0;   // the grid writer's work counters
     int* scell = reinterpret_cast<int*>(skeys + P);
     __shared__ int swarp_heads[kPrepThreads / 32];
     __shared__ int swarp_valid[kPrepThreads / 32];
@@ -314,6 +315,8 @@ vox_front_kernel(const float* __restrict__ points, int pstride, float* __restric
     const int nch = min(kMeanChans, C - c0);
     const VoxWs L = vox_ws_layout(N, ntiles);
     int* W = ws + (size_t)b * L.stride;
+    if (b == 0 && g == 0 && tid < 2 * kMaxFillCalls)            // the grid writer's work counters: behind the means table
+        reinterpret_cast<int*>(means + (size_t)gridDim.y * C * ucap)[tid] = 0;
 
     // ---- this CTA's feature rows start flowing into shared memory now; they are first needed after the sort
     {
@@ -525,164 +528,180 @@ vox_front_kernel(const float* __restrict__ points, int pstride, float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ K3
-// One occupied cell ("segment" of the cell-sorted point list) of the current tile, as cached by its thread.
-struct SegRegs { int off, sg, cnt; };      // offset inside the tile, slot in the cloud's cell table, point count
+// The dense grid [C, r^3] (+ the count grid as plane C) of every cloud, written exactly once, by WARPS THAT EACH RUN THEIR OWN
+// PIPELINE: a warp owns kFwSlots shared-memory tiles of kTileCells floats (8 KB), zeroed once; per (cloud, tile, plane)
+// it writes the tile's few occupied cells into the next slot (values from the compact means table), and one lane ships
+// the slot with ONE cp.async.bulk shared -> global (TMA engine, SASS UBLKCP).  No CTA barrier anywhere: the slot is
+// guarded by the issuing lane's own bulk-group counter (wait_group.read) and two __syncwarp().  The CTA-synchronous
+// form this replaces (256 threads around a 3 x 32 KB ring, two __syncthreads per tile) reached 5.1 TB/s alone and fell
+// to 3 TB/s with k-NN warps competing for issue slots on the same SM — every barrier waited for the slowest of 8 warps;
+// autonomous warps stall only themselves, and a micro-benchmark of the bare pattern (tools/exp_fillwarp.cu) streams at
+// 6.0-6.1 TB/s with as little as 4 warps x 2 x 8 KB per SM.
+// Work items = (cloud, tile, group of kPlaneGroup planes) from one global counter (a warp that becomes resident late
+// simply takes fewer).  A warp keeps the tile's cell list (offset in the tile, table slot, point count) in registers and
+// prefetches the NEXT item's list while it ships the current one.  Slots are never re-zeroed wholesale: the cells of the
+// previous item's tile are cleared lazily, slot by slot, right before each slot's first reuse.
+struct FillItem { int bt, b, t, p0, p1, sA, sB; };      // (cloud, tile) id, cloud, tile, plane range, the tile's table slots
 
-template <int RING>
-__global__ void __maxnreg__(kFillMaxRegs)
+__device__ __forceinline__ void fill_item_decode(FillItem& it, int item, int total_items, int groups, int pgroup, int planes,
+                                                 int ntiles, int b0, const int* __restrict__ ws, const VoxWs& L)
+{
+    it.bt = -1; it.b = it.t = it.p0 = it.p1 = it.sA = it.sB = 0;
+    if (item >= total_items) return;
+    it.bt = item / groups;
+    it.p0 = (item - it.bt * groups) * pgroup;
+    it.p1 = min(planes, it.p0 + pgroup);
+    it.t = it.bt % ntiles;
+    it.b = b0 + it.bt / ntiles;
+    const int* W = ws + (size_t)it.b * L.stride;
+    it.sA = __ldg(W + L.off_tile + it.t);
+    it.sB = __ldg(W + L.off_tile + it.t + 1);
+}
+
+template <int SLOTS>
+__global__ void __launch_bounds__(32 * kFwMaxWarps)
 vox_fill_kernel(const float* __restrict__ means, const int* __restrict__ ws, int b0, int B, int C, int N, int s,
-                int tile_cells, int ntiles, int ucap, int* __restrict__ work_counter,
+                int tile_cells, int ntiles, int ucap, int pgroup, int kListCap, int* __restrict__ work_counter,
                 float* __restrict__ out, int* __restrict__ cnt)
 {
-    extern __shared__ __align__(128) float sring[];        // RING tiles of tile_cells floats
-    __shared__ int s_item[2];
-    const int tid = threadIdx.x;
+    const int kFwWarps = blockDim.x >> 5;
+    // per warp: SLOTS tiles of tile_cells floats | 3 cell-id lists (previous / current / next item) | 2 value rows (this / next plane)
+    extern __shared__ __align__(128) float sring[];
+    const int lane = threadIdx.x & 31;
+    const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int per_warp = SLOTS * tile_cells + 5 * kListCap;
+    float* ring = sring + (size_t)wid * per_warp;
+    int* lists = reinterpret_cast<int*>(ring + SLOTS * tile_cells);      // [3][kListCap]
+    float* rows = ring + SLOTS * tile_cells + 3 * kListCap;               // [2][kListCap]
     const VoxWs L = vox_ws_layout(N, ntiles);
     const int planes = C + 1;                              // plane C is the integer count grid
-
-    // Work items = (cloud, tile, group of kPlaneGroup planes), handed out through one global counter, plane group
-    // fastest: a CTA that draws consecutive numbers usually stays on the same (cloud, tile) and keeps its cached cell
-    // table.  Dynamic hand-out instead of a static slice per CTA: when this kernel shares the SMs with the k-NN branch
-    // some of its CTAs only become resident late — they then simply take fewer items, the kernel does not wait for them.
-    const int groups = (planes + kPlaneGroup - 1) / kPlaneGroup;
+    const int groups = (planes + pgroup - 1) / pgroup;
     const int total_items = B * ntiles * groups;
-    if (tid == 0) s_item[0] = atomicAdd(work_counter, 1);
-    for (int i = tid; i < RING * tile_cells / 4; i += kFillThreads)
-        reinterpret_cast<float4*>(sring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
+    const int nwarps = gridDim.x * kFwWarps;
+
+    for (int i = lane; i < SLOTS * tile_cells / 4; i += 32) reinterpret_cast<float4*>(ring)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // Everything a plane needs arrives in shared memory by cp.async — no registers, any number of cells in flight at once:
+    // the cell ids of an item's tile once per item, the tile's row of the compact means table once per plane.
+    auto list_fetch = [&](const FillItem& it, int* dst) {
+        if (it.bt >= 0) {
+            const int* src = ws + (size_t)it.b * L.stride + L.off_cell + it.sA;
+            const int n = min(it.sB - it.sA, kListCap);
+            for (int i = lane; i < n; i += 32) cp_async4(dst + i, src + i);
+        }
+    };
+    auto row_fetch = [&](const FillItem& it, int p, float* dst) {
+        if (it.bt >= 0 && p < it.p1) {
+            const int n = min(it.sB - it.sA, kListCap);
+            if (p < C) {
+                const float* src = means + ((size_t)it.b * C + p) * ucap + it.sA;
+                for (int i = lane; i < n; i += 32) cp_async4(dst + i, src + i);
+            } else {                                       // the count plane: point counts from the table's start offsets
+                const int* S = ws + (size_t)it.b * L.stride + L.off_start + it.sA;
+                for (int i = lane; i < n; i += 32) dst[i] = __int_as_float(__ldg(S + i + 1) - __ldg(S + i));
+            }
+        }
+    };
+    auto commit = [] { asm volatile("cp.async.commit_group;" ::: "memory"); };
+
+    // Work items = (cloud, tile, group of `pgroup` planes), plane group fastest.  A plane-tile is NOT a constant amount of
+    // work — spherical grids put most of a cloud's cells into one or two tiles — so the items are drawn from a global
+    // counter (cutting the work into equal static runs per warp measured 87 us against 59 on the spherical grid, and 4.7
+    // against 6.8 TB/s at r = 64).  The first item of every warp is its own number: no round trip to the counter before
+    // the first store; the counter hands out the items from nwarps on.
+    const int id0 = blockIdx.x * kFwWarps + wid;
+    int id1 = 0;
+    if (lane == 0) id1 = nwarps + atomicAdd(work_counter, 1);
+    FillItem cur, nxt;
+    fill_item_decode(cur, id0, total_items, groups, pgroup, planes, ntiles, b0, ws, L);
+    int lc = 0;                                             // current item's list; (lc + 2) % 3 = previous, (lc + 1) % 3 = next
+    int rc = 0;                                             // value row of the plane about to be shipped
+    list_fetch(cur, lists + lc * kListCap);
+    row_fetch(cur, cur.p0, rows + rc * kListCap);
+    commit();
+    int next_id = __shfl_sync(0xffffffffu, id1, 0);
 
     int slot = 0;
-    // The ring slots are never re-zeroed wholesale.  Between two bulk copies out of a slot only the occupied cells
-    // of the tile are rewritten; when the CTA moves on to another (cloud, tile) the cells of the PREVIOUS tile are
-    // cleared lazily, slot by slot, right before each slot's first reuse — so the copies still in flight are never
-    // waited for (no pipeline drain at a tile switch).
-    SegRegs seg[kSegCache];                                 // this tile's cells owned by this thread
-    int old_off[kSegCache];                                 // previous tile's cells (offset, or -1)
-#pragma unroll
-    for (int q = 0; q < kSegCache; ++q) { seg[q].off = 0; seg[q].sg = 0; seg[q].cnt = 0; old_off[q] = -1; }
-    int extra_lo = 0, extra_hi = 0, cur_cell_lo = 0;        // cells beyond the register cache (rare), current tile
-    int old_extra_lo = 0, old_extra_hi = 0, old_cell_lo = 0;
-    const int* curW = nullptr;
-    const int* oldW = nullptr;
-    int cur_bt = -1;
-    int stale = 0;                                          // ring slots that still carry the previous tile's cells
-    int planes_here = RING;                                // planes shipped since the last tile switch
+    int stale = 0;                                          // slots that still carry the previous item's cells
+    int old_n = 0, old_sA = 0, old_cell_lo = 0;
+    const int* oldW = ws;
 
-    auto unpatch_slot = [&](float* tile) {
-#pragma unroll
-        for (int q = 0; q < kSegCache; ++q)
-            if (old_off[q] >= 0) tile[old_off[q]] = 0.f;
-        for (int sg = old_extra_lo + tid; sg < old_extra_hi; sg += kFillThreads)
-            tile[__ldg(oldW + L.off_cell + sg) - old_cell_lo] = 0.f;
-    };
+    while (cur.bt >= 0) {
+        // two items ahead: the atomic's reply is not needed before the end of this item; one item ahead: its tile header is
+        // requested now and needed at this item's last plane
+        int after = 0;
+        if (lane == 0) after = nwarps + atomicAdd(work_counter, 1);
+        fill_item_decode(nxt, next_id, total_items, groups, pgroup, planes, ntiles, b0, ws, L);
 
-    for (int it = 0;; it ^= 1) {
-        const int item = s_item[it];
-        if (item >= total_items) break;
-        if (tid == 0) s_item[it ^ 1] = atomicAdd(work_counter, 1);      // next item; read after this item's barriers
-        const int bt = item / groups;
-        const int p0 = (item - bt * groups) * kPlaneGroup;
-        const int p1 = min(planes, p0 + kPlaneGroup);
-        const int t = bt % ntiles;
-        const int b = b0 + bt / ntiles;                    // B clouds starting at b0
-        const int* W = ws + (size_t)b * L.stride;
-        const int cell_lo = t * tile_cells;
+        const int* W = ws + (size_t)cur.b * L.stride;
+        const int cell_lo = cur.t * tile_cells;
         const int ncell = min(tile_cells, s - cell_lo);
+        const int n = cur.sB - cur.sA;                      // occupied cells of this tile
+        const int nl = min(n, kListCap);
+        const int* clist = lists + lc * kListCap;
+        const int* olist = lists + ((lc + 2) % 3) * kListCap;
 
-        if (bt != cur_bt) {
-            const int sA = __ldg(W + L.off_tile + t), sB = __ldg(W + L.off_tile + t + 1);
-            if (curW != nullptr) {
-                if (stale > 0 || planes_here < RING) {
-                    // the previous tile did not cycle through the whole ring: clean everything the slow way
-                    if (tid == 0) ri_bulk_wait_read<0>();
-                    __syncthreads();
-                    for (int k2 = 0; k2 < RING; ++k2) {
-                        float* tile = sring + k2 * tile_cells;
-                        if (stale > 0) unpatch_slot(tile);
-#pragma unroll
-                        for (int q = 0; q < kSegCache; ++q)
-                            if (seg[q].cnt > 0) tile[seg[q].off] = 0.f;
-                        for (int sg = extra_lo + tid; sg < extra_hi; sg += kFillThreads)
-                            tile[__ldg(curW + L.off_cell + sg) - cur_cell_lo] = 0.f;
-                    }
-                    __syncthreads();
-                    stale = 0;
-#pragma unroll
-                    for (int q = 0; q < kSegCache; ++q) old_off[q] = -1;
-                    old_extra_lo = old_extra_hi = 0;
-                } else {
-#pragma unroll
-                    for (int q = 0; q < kSegCache; ++q) old_off[q] = seg[q].cnt > 0 ? seg[q].off : -1;
-                    old_extra_lo = extra_lo; old_extra_hi = extra_hi; old_cell_lo = cur_cell_lo; oldW = curW;
-                    stale = RING;
-                }
+        for (int p = cur.p0; p < cur.p1; ++p) {
+            // request the NEXT plane's values (or the next item's list and first row) before touching this plane
+            if (p + 1 < cur.p1) row_fetch(cur, p + 1, rows + (rc ^ 1) * kListCap);
+            else { list_fetch(nxt, lists + ((lc + 1) % 3) * kListCap); row_fetch(nxt, nxt.p0, rows + (rc ^ 1) * kListCap); }
+            commit();
+            float* tile = ring + slot * tile_cells;
+            if (lane == 0) ri_bulk_wait_read<SLOTS - 1>();        // the copy that last used this slot has left shared memory
+            asm volatile("cp.async.wait_group 1;" ::: "memory");  // this plane's values (and this item's list) have landed
+            __syncwarp();
+            if (stale > 0) {                                       // first reuse of this slot since the item switch
+                for (int i = lane; i < old_n; i += 32)
+                    tile[(i < kListCap ? olist[i] : __ldg(oldW + L.off_cell + old_sA + i)) - old_cell_lo] = 0.f;
+                --stale;
+                __syncwarp();                                      // an old cell of one lane may be a new cell of another
             }
-            // this tile's table entries -> registers
-#pragma unroll
-            for (int q = 0; q < kSegCache; ++q) {
-                const int sg = sA + tid + q * kFillThreads;
-                seg[q].cnt = 0;
-                if (sg < sB) {
-                    seg[q].off = __ldg(W + L.off_cell + sg) - cell_lo;
-                    seg[q].sg = sg;
-                    seg[q].cnt = __ldg(W + L.off_start + sg + 1) - __ldg(W + L.off_start + sg);
-                }
+            const float* row = rows + rc * kListCap;
+            for (int i = lane; i < nl; i += 32) tile[clist[i] - cell_lo] = row[i];
+            for (int i = kListCap + lane; i < n; i += 32) {       // more cells in one tile than the lists hold
+                const float x = p < C ? __ldg(means + ((size_t)cur.b * C + p) * ucap + cur.sA + i)
+                                      : __int_as_float(__ldg(W + L.off_start + cur.sA + i + 1) - __ldg(W + L.off_start + cur.sA + i));
+                tile[__ldg(W + L.off_cell + cur.sA + i) - cell_lo] = x;
             }
-            extra_lo = min(sB, sA + kSegCache * kFillThreads); extra_hi = sB; cur_cell_lo = cell_lo; curW = W;
-            cur_bt = bt;
-            planes_here = 0;
+            ri_fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                void* dst = (p < C) ? (void*)(out + ((size_t)cur.b * C + p) * s + cell_lo)
+                                    : (void*)(cnt + (size_t)cur.b * s + cell_lo);
+                ri_bulk_store(dst, tile, (uint32_t)ncell * 4u);
+                ri_bulk_commit();
+            }
+            slot = (slot + 1 == SLOTS) ? 0 : slot + 1;
+            rc ^= 1;
         }
-        planes_here += p1 - p0;
-        const float* Mb = means + (size_t)b * C * ucap;
-
-        // Planes are handled in batches of kPlaneBatch: the table reads of a whole batch (independent, coalesced
-        // loads, one per plane and cell) are issued together, so their latency is paid once per batch.
-        for (int pb = p0; pb < p1; pb += kPlaneBatch) {
-            float val[kSegCache][kPlaneBatch];
-#pragma unroll
-            for (int q = 0; q < kSegCache; ++q) {
-#pragma unroll
-                for (int j = 0; j < kPlaneBatch; ++j) {
-                    const int p = pb + j;
-                    val[q][j] = 0.f;
-                    if (seg[q].cnt > 0 && p < p1)
-                        val[q][j] = p < C ? __ldg(Mb + (size_t)p * ucap + seg[q].sg) : __int_as_float(seg[q].cnt);
-                }
+        // item switch.  Slots not reused since the LAST switch still hold the cells of the item before this one (only an item
+        // of fewer planes than slots leaves such slots): two generations cannot be tracked lazily — clean everything now.
+        if (stale > 0) {
+            if (lane == 0) ri_bulk_wait_read<0>();
+            __syncwarp();
+            for (int k2 = 0; k2 < SLOTS; ++k2) {
+                float* tile = ring + k2 * tile_cells;
+                for (int i = lane; i < old_n; i += 32)
+                    tile[(i < kListCap ? olist[i] : __ldg(oldW + L.off_cell + old_sA + i)) - old_cell_lo] = 0.f;
+                for (int i = lane; i < n; i += 32)
+                    tile[(i < kListCap ? clist[i] : __ldg(W + L.off_cell + cur.sA + i)) - cell_lo] = 0.f;
             }
-#pragma unroll
-            for (int j = 0; j < kPlaneBatch; ++j) {
-                const int p = pb + j;
-                if (p >= p1) break;
-                float* tile = sring + slot * tile_cells;
-                if (tid == 0) ri_bulk_wait_read<RING - 1>();  // the copy that last used this slot has left smem
-                __syncthreads();
-                if (stale > 0) {                                // first reuse of this slot since the tile switch
-                    unpatch_slot(tile);
-                    --stale;
-                    __syncthreads();                            // an old cell may coincide with a new one of another thread
-                }
-#pragma unroll
-                for (int q = 0; q < kSegCache; ++q)
-                    if (seg[q].cnt > 0) tile[seg[q].off] = val[q][j];
-                for (int sg = extra_lo + tid; sg < extra_hi; sg += kFillThreads) {      // beyond the register cache
-                    const int off = __ldg(W + L.off_cell + sg) - cell_lo;
-                    tile[off] = p < C ? __ldg(Mb + (size_t)p * ucap + sg)
-                                      : __int_as_float(__ldg(W + L.off_start + sg + 1) - __ldg(W + L.off_start + sg));
-                }
-                ri_fence_proxy_async_smem();
-                __syncthreads();
-                if (tid == 0) {
-                    void* dst = (p < C) ? (void*)(out + ((size_t)b * C + p) * s + cell_lo)
-                                        : (void*)(cnt + (size_t)b * s + cell_lo);
-                    ri_bulk_store(dst, tile, (uint32_t)ncell * 4u);
-                    ri_bulk_commit();
-                }
-                slot = (slot + 1 == RING) ? 0 : slot + 1;
-            }
-        }
-        __syncthreads();                                        // s_item[it ^ 1] is visible; s_item[it] may be rewritten
+            __syncwarp();
+            stale = 0; old_n = 0;
+        } else if (nxt.bt != cur.bt) {
+            old_n = n; old_sA = cur.sA; old_cell_lo = cell_lo; oldW = W;
+            stale = SLOTS;
+        }                                                        // same (cloud, tile) next: its planes overwrite the same cells
+        lc = (lc + 1) % 3;                                        // next -> current -> previous
+        cur = nxt;
+        next_id = __shfl_sync(0xffffffffu, after, 0);
     }
-    if (tid == 0) ri_bulk_wait<0>();
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (lane == 0) {
+        ri_bulk_wait<0>();
+        // the last warp of the launch to run out of work resets the counters: the next launch on this workspace finds zeros
+        if (atomicAdd(work_counter + 1, 1) == nwarps - 1) { work_counter[1] = 0; __threadfence(); work_counter[0] = 0; }
+    }
 }
 
 // --------------------------------------------------------------------------------------- fallback path
@@ -726,6 +745,11 @@ vox_scatter_atomic_kernel(const float* __restrict__ feat, const int* __restrict_
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 struct VoxPlan { bool tiled; int tile_cells, ntiles, P; VoxWs L; };
+inline int vox_tile_cells()
+{
+    const int v = ri_env().fill_tile_cells;
+    return (v >= 256 && v <= 16384 && v % 4 == 0) ? v : kTileCells;
+}
 
 VoxPlan vox_plan(int N, int r, const void* out, const void* cnt)
 {
@@ -733,29 +757,35 @@ VoxPlan vox_plan(int N, int r, const void* out, const void* cnt)
     const long long s = (long long)r * r * r;
     p.tiled = N <= kSmallCloudMax && (s % 4 == 0) &&
               ((uintptr_t)out % 16 == 0) && ((uintptr_t)cnt % 16 == 0);
-    p.tile_cells = (int)(s < kTileCells ? s : kTileCells);
+    const int tc = vox_tile_cells();
+    p.tile_cells = (int)(s < tc ? s : tc);
     p.ntiles = (int)((s + p.tile_cells - 1) / p.tile_cells);
     p.P = next_pow2(N < 2 ? 2 : N);
     p.L = vox_ws_layout(N, p.ntiles);
     return p;
 }
 
+// work counters of the grid writer: behind the compact means table
+inline int* vox_fill_counters(int* ws, const VoxPlan& plan, int B, int C, int N)
+{
+    float* means = reinterpret_cast<float*>(ws + (size_t)B * plan.L.stride);
+    return reinterpret_cast<int*>(means + (size_t)B * C * ((N + 3) / 4 * 4));
+}
+
 size_t vox_ws_need(const VoxPlan& plan, int B, int C, int N)
 {
     return (size_t)B * plan.L.stride * sizeof(int) + (size_t)B * C * ((N + 3) / 4 * 4) * sizeof(float) +
-           kMaxFillCalls * sizeof(int);                    // work counters of the fill launches
+           2 * kMaxFillCalls * sizeof(int);                // work counters of the fill launches
 }
 
 // K1 for all B clouds: ind + the per-cloud cell tables in the workspace
 template <bool SPH>
-int vox_prepare_launch(const void* coords, int B, int N, int r, int s, const VoxPlan& plan, int* ind, int* ws, cudaStream_t st)
+int vox_prepare_launch(const void* coords, int B, int C, int N, int r, int s, const VoxPlan& plan, int* ind, int* ws, cudaStream_t st)
 {
     const size_t smem1 = (size_t)plan.P * (sizeof(unsigned long long) + sizeof(int));
-    if (smem1 + 1024 > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(vox_prepare_kernel<SPH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-        if (e != cudaSuccess) return (int)e;
-    }
-    vox_prepare_kernel<SPH><<<B, kPrepThreads, smem1, st>>>(coords, N, plan.P, r, s, plan.tile_cells, plan.ntiles, ind, ws);
+    RI_KERNEL_SETUP(vox_prepare_kernel<SPH>, true, ri_step_carveout_percent());
+    vox_prepare_kernel<SPH><<<B, kPrepThreads, smem1, st>>>(coords, N, plan.P, r, s, plan.tile_cells, plan.ntiles, ind, ws,
+                                                            vox_fill_counters(ws, plan, B, C, N));
     RI_LAUNCH_CHECK();
     return RI_OK;
 }
@@ -769,20 +799,11 @@ int vox_means_launch(const float* feat, int B, int C, int N, int b0, int b1, con
     const int ucap = (N + 3) / 4 * 4;
     const int nb = b1 - b0;
     if (nb <= 0 || C <= 0) return RI_OK;
-    static bool carveout_set = false;
-    if (!carveout_set) {
-        ri_prefer_step_carveout(vox_means_kernel);
-        ri_prefer_step_carveout(vox_prepare_kernel<true>); ri_prefer_step_carveout(vox_prepare_kernel<false>);
-        carveout_set = true;
-    }
     dim3 gm((C + kMeanChans - 1) / kMeanChans, nb);
     // feature rows always staged (<= 128 KB at N = 4096); the means copy only while the CTA stays under ~100 KB
     const int smem_means = (edge != nullptr && (size_t)kMeanChans * (N + 1 + ucap) * sizeof(float) <= 100 * 1024) ? 1 : 0;
     const size_t smem_m = (size_t)kMeanChans * (N + 1 + (smem_means ? ucap : 0)) * sizeof(float);
-    if (smem_m > 48 * 1024) {
-        cudaError_t em = cudaFuncSetAttribute(vox_means_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
-        if (em != cudaSuccess) return (int)em;
-    }
+    RI_KERNEL_SETUP(vox_means_kernel, true, ri_step_carveout_percent());
     vox_means_kernel<<<gm, kMeanThreads, smem_m, st>>>(feat, ws, b0, C, N, plan.ntiles, ucap, smem_means, means, edge);
     RI_LAUNCH_CHECK();
     return RI_OK;
@@ -796,26 +817,36 @@ int vox_fill_launch(int B, int C, int N, int s, int b0, int b1, const VoxPlan& p
     const int ucap = (N + 3) / 4 * 4;
     const int nb = b1 - b0;
     if (nb <= 0) return RI_OK;
-    // one work counter per fill launch; slot chosen by the first cloud so that chunked launches never share one
-    int* counter = reinterpret_cast<int*>(means + (size_t)B * C * ucap) + (b0 % kMaxFillCalls);
-    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), st);
-    if (e != cudaSuccess) return (int)e;
+    // A pair of work counters (items drawn, warps finished) per fill launch, slot chosen by the first cloud.  They are
+    // zeroed by the prepare step of the workspace and again by every fill launch when its last warp retires, so no memset
+    // is enqueued here.  Launches that may overlap in time must not share a slot: keep the fills of one workspace on one
+    // stream (or their b0 distinct modulo kMaxFillCalls).
+    // Footprint: 4 warps x (2 x 8 KB tiles + 5 x 768 x 4 B of lists and rows) = 124 KB, 128 threads x 96 registers.
+    // Measured (tools/tune_lanes.py, 32 x 1024, r = 32, two batches in flight; grid writer alone / step one at a time / in flight):
+    //   4 warps, 768-entry lists (124 KB)   cu_dg 60.6 / 166 / 144.9 us   sph_dg 59.3 / 137 / 120.8 us      <- default
+    //   3 warps, 768-entry lists ( 93 KB)   cu_dg 68.3 / 175 / 140.7 us   sph_dg 65.4 / 142 / 121 us
+    //   4 warps, 1024-entry lists (144 KB)  cu_dg 60.5 / 166 / 155.4 us   sph_dg 59.4 / 136 / 128.6 us
+    // (the smaller the writer, the more often it shares an SM with the streaming devoxelizer or the prefix kernel of the
+    // other batch in flight); 512-entry lists send the crowded tiles of the spherical grid down the slow path (78 us alone).
+    int* counter = vox_fill_counters(ws, plan, B, C, N) + 2 * (b0 % kMaxFillCalls);
+    const RiEnv& env = ri_env();
     const int sms = ri_num_sms();
-    int ring = kRing, ctas_per_sm = kFillCtasPerSm;
-    if (const char* ev = getenv("RI_FILL_RING")) { const int v = atoi(ev); if (v >= 3 && v <= 6) ring = v; }
-    if (const char* ev = getenv("RI_FILL_CTAS")) { const int v = atoi(ev); if (v >= 1 && v <= 2) ctas_per_sm = v; }
-    size_t smem2 = (size_t)ring * plan.tile_cells * sizeof(float);
-    if (const char* ev = getenv("RI_FILL_PAD_KB")) { const int v = atoi(ev); if (v >= 0 && v <= 64) smem2 += (size_t)v << 10; }
-    auto kern = ring == 3 ? vox_fill_kernel<3> : ring == 4 ? vox_fill_kernel<4> : ring == 5 ? vox_fill_kernel<5> : vox_fill_kernel<6>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    if (e != cudaSuccess) return (int)e;
-    ri_prefer_step_carveout(kern);
-    const long long items = (long long)nb * plan.ntiles * ((C + 1 + kPlaneGroup - 1) / kPlaneGroup);
+    const int ctas_per_sm = (env.fill_ctas >= 1 && env.fill_ctas <= 4) ? env.fill_ctas : kFillCtasPerSm;
+    const int slots = (env.fill_ring >= 2 && env.fill_ring <= 4) ? env.fill_ring : kFwSlots;
+    const int warps = (env.fill_warps >= 1 && env.fill_warps <= kFwMaxWarps) ? env.fill_warps : kFwWarps;
+    const int listcap = (env.fill_listcap >= 32 && env.fill_listcap <= 4096) ? (env.fill_listcap + 3) / 4 * 4 : kListCapDefault;
+    size_t smem2 = (size_t)warps * ((size_t)slots * plan.tile_cells + 5 * listcap) * sizeof(float);
+    if (env.fill_pad_kb >= 0 && env.fill_pad_kb <= 64) smem2 += (size_t)env.fill_pad_kb << 10;
+    auto kern = slots == 2 ? vox_fill_kernel<2> : slots == 3 ? vox_fill_kernel<3> : vox_fill_kernel<4>;
+    RI_KERNEL_SETUP(kern, true, ri_step_carveout_percent());
+    const int pgroup = (env.fill_group >= slots && env.fill_group <= 64) ? env.fill_group : kPlaneGroup;
+    const long long items = (long long)nb * plan.ntiles * ((C + 1 + pgroup - 1) / pgroup);
     if (items > 0x7fffffffLL) return RI_ERR_UNSUPPORTED;
     long long grid = (long long)ctas_per_sm * sms;
-    if (grid > items) grid = items;
-    kern<<<(unsigned)grid, kFillThreads, smem2, st>>>(means, ws, b0, nb, C, N, s, plan.tile_cells, plan.ntiles,
-                                                      ucap, counter, out, cnt);
+    const long long want = (items + warps - 1) / warps;
+    if (grid > want) grid = want;
+    kern<<<(unsigned)grid, 32 * warps, smem2, st>>>(means, ws, b0, nb, C, N, s, plan.tile_cells, plan.ntiles,
+                                                    ucap, pgroup, listcap, counter, out, cnt);
     RI_LAUNCH_CHECK();
     return RI_OK;
 }
@@ -883,8 +914,10 @@ vox_table_count_kernel(const unsigned* __restrict__ keys, int N, int s, int nchu
     }
 }
 
-__global__ void vox_table_scan_kernel(int N, int ntiles, int nchunks, int* __restrict__ chunk_counts, int* __restrict__ ws)
+__global__ void vox_table_scan_kernel(int N, int ntiles, int nchunks, int* __restrict__ chunk_counts, int* __restrict__ ws,
+                                      int* __restrict__ fill_counters)
 {
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i < 2 * kMaxFillCalls; i += blockDim.x) fill_counters[i] = 0;
     const int b = blockIdx.x;
     if (threadIdx.x != 0) return;
     const VoxWs L = vox_ws_layout(N, ntiles);
@@ -1033,7 +1066,7 @@ int voxelize_impl(const float* feat, const void* coords, int B, int C, int N, in
     if (plan.tiled && N > 0) {
         if (workspace == nullptr || ws_bytes < vox_ws_need(plan, B, C, N)) return RI_ERR_WORKSPACE;
         int* ws = reinterpret_cast<int*>(workspace);
-        const int rc = vox_prepare_launch<SPH>(coords, B, N, r, s, plan, ind, ws, st);
+        const int rc = vox_prepare_launch<SPH>(coords, B, C, N, r, s, plan, ind, ws, st);
         if (rc != RI_OK) return rc;
         const int rc2 = vox_means_launch(feat, B, C, N, 0, B, plan, edge, ws, st);
         if (rc2 != RI_OK) return rc2;
@@ -1041,7 +1074,7 @@ int voxelize_impl(const float* feat, const void* coords, int B, int C, int N, in
     }
     // scan-sized clouds: global sort + the same means / grid-writer phases (deterministic); needs the larger workspace
     if (N > kSmallCloudMax && (s_ll % 4 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)cnt % 16 == 0) && B <= 65535 &&
-        C <= 65535 && workspace != nullptr && getenv("RI_VOX_ATOMIC") == nullptr) {
+        C <= 65535 && workspace != nullptr && !ri_env().vox_atomic) {
         VoxLarge V;
         const size_t base = vox_ws_need(plan, B, C, N);
         if (vox_large_layout(B, N, s_ll, base, V) && ws_bytes >= V.total) {
@@ -1059,7 +1092,7 @@ int voxelize_impl(const float* feat, const void* coords, int B, int C, int N, in
             if (ec != cudaSuccess) return (int)ec;
             int* chunks = reinterpret_cast<int*>(wb + V.chunks);
             vox_table_count_kernel<<<dim3(V.nchunks, B), kLgChunk, 0, st>>>(keys_out, N, s, V.nchunks, chunks);
-            vox_table_scan_kernel<<<B, 32, 0, st>>>(N, plan.ntiles, V.nchunks, chunks, ws);
+            vox_table_scan_kernel<<<B, 32, 0, st>>>(N, plan.ntiles, V.nchunks, chunks, ws, vox_fill_counters(ws, plan, B, C, N));
             vox_table_write_kernel<<<dim3(V.nchunks, B), kLgChunk, 0, st>>>(keys_out, vals_out, N, s, plan.ntiles, V.nchunks, chunks, ws);
             vox_table_tiles_kernel<<<dim3((plan.ntiles + 256) / 256, B), 256, 0, st>>>(N, plan.tile_cells, plan.ntiles, ws);
             RI_LAUNCH_CHECK();
@@ -1103,11 +1136,12 @@ extern "C" size_t ri_voxelize_workspace_bytes(int B, int C, int N, int r)
     if (B <= 0 || N <= 0 || r <= 0) return 16;
     if (C < 0) C = 0;
     const long long s = (long long)r * r * r;
-    const int tile_cells = (int)(s < kTileCells ? s : kTileCells);
+    const int tc = vox_tile_cells();
+    const int tile_cells = (int)(s < tc ? s : tc);
     const int ntiles = (int)((s + tile_cells - 1) / tile_cells);
     size_t need = (size_t)B * vox_ws_layout(N, ntiles).stride * sizeof(int) +     // per-cloud tables
                   (size_t)B * C * ((N + 3) / 4 * 4) * sizeof(float) +            // compact cell means [B][C][<=N]
-                  kMaxFillCalls * sizeof(int) + 16;                               // work counters
+                  2 * kMaxFillCalls * sizeof(int) + 16;                           // work counters
     if (N > kSmallCloudMax) {                                                     // scan-sized clouds: sort buffers
         VoxLarge V;
         if (vox_large_layout(B, N, s, need, V)) need = V.total + 16;
@@ -1161,7 +1195,7 @@ static int prepare_entry(const void* coords, int B, int C, int N, int r, int* in
     const VoxPlan plan = vox_plan(N, r, nullptr, nullptr);
     if (!plan.tiled) return RI_ERR_UNSUPPORTED;
     if (workspace == nullptr || ws_bytes < vox_ws_need(plan, B, C, N)) return RI_ERR_WORKSPACE;
-    return vox_prepare_launch<SPH>(coords, B, N, r, (int)s_ll, plan, ind, reinterpret_cast<int*>(workspace), (cudaStream_t)stream);
+    return vox_prepare_launch<SPH>(coords, B, C, N, r, (int)s_ll, plan, ind, reinterpret_cast<int*>(workspace), (cudaStream_t)stream);
 }
 
 extern "C" int ri_sph_voxelize_prepare_f32(const float* coords, int B, int C, int N, int r, int* ind,
@@ -1227,9 +1261,7 @@ extern "C" int ri_vox_front_f32(const float* points, int pstride, const float* m
     const size_t smem = (size_t)plan.P * (sizeof(unsigned long long) + sizeof(int)) + (size_t)(3 * N + 2) * sizeof(int) +
                         (size_t)kMeanChans * (N + 4 + ucap) * sizeof(float);
     auto kern = shape == 2 ? vox_front_kernel<true> : vox_front_kernel<false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    ri_prefer_step_carveout(kern);
+    RI_KERNEL_SETUP(kern, true, ri_step_carveout_percent());
     dim3 grid(C > 0 ? (C + kMeanChans - 1) / kMeanChans : 1, B);
     // norm_mode bit 8: compute the per-cloud mean inside the kernel (torch's reduction order) and write it to `mean`
     // norm_mode bit 9: `edge` is [B,C,N] and receives only the feat - mean(cell) half of the edge features
