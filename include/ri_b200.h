@@ -14,7 +14,10 @@
  *     enqueued on that stream and the call returns without synchronising;
  *   - return value: 0 on success, a positive cudaError_t if a launch failed, or a negative RI_ERR_* code for a bad
  *     argument.  Never calls exit() (the reference's CUDA_CHECK_ERRORS does, cuda_utils.cuh:28-37);
- *   - re-entrant, no global state besides a cached SM count.
+ *   - re-entrant and thread-safe: the only process-wide state is read-only after its first use — the environment knobs of
+ *     DESIGN.md §11 (read once), the SM count per device, and the per-(kernel, device) record that a kernel's function
+ *     attributes have been set (csrc/ri_common.cuh).  Several host threads may call into the library on several devices;
+ *   - calls that share a WORKSPACE must be ordered on one stream (the workspace holds their intermediate tables).
  */
 #ifndef RI_B200_H
 #define RI_B200_H

@@ -149,10 +149,7 @@ extern "C" int ri_ball_query_f32(const float* centers, const float* points, int 
     const float r2 = radius * radius;                              // ball_query.cpp:24
     const int centres_per_cta = 8 * (kBqThreads / 32);             // 8 centres per warp
     const size_t smem = (size_t)(N < kBqTile ? N : kBqTile) * sizeof(float4);
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(ball_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
+    RI_KERNEL_SETUP(ball_query_kernel, true, -1);
     dim3 grid((M + centres_per_cta - 1) / centres_per_cta, B);
     ball_query_kernel<<<grid, kBqThreads, smem, st>>>(centers, points, N, M, r2, U, centres_per_cta, neighbors);
     RI_LAUNCH_CHECK();
@@ -241,10 +238,7 @@ extern "C" int ri_local_ppf_f32(const float* points_coords, const float* points_
     if (N == 0) return RI_ERR_BAD_ARG;
     const size_t smem = (size_t)kLpCentres * (U + 1) * sizeof(int);
     if (smem > 200 * 1024) return RI_ERR_UNSUPPORTED;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(local_ppf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
+    RI_KERNEL_SETUP(local_ppf_kernel, true, -1);
     dim3 grid((M + kLpCentres - 1) / kLpCentres, B);
     local_ppf_kernel<<<grid, kLpThreads, smem, (cudaStream_t)stream>>>(points_coords, points_normals, centers_coords,
                                                                       centers_normals, neighbors, N, M, U, out);

@@ -143,13 +143,39 @@ gs_reduce_kernel(const float* __restrict__ pts, const float* __restrict__ feats,
             for (int s = s0; s < s1; ++s) acc = __fadd_rn(acc, feats[(size_t)order[s] * fdim + f]);
             out_feats[(size_t)cell * fdim + f] = __fdiv_rn(acc, (float)cnt);                    // f / (float)count
         } else {
+            // most frequent label of the cell, the smallest one among equally frequent ones.  Small cells: count every label
+            // against the cell (cnt^2 <= 4096 compares).  Large cells (a coarse grid on a 50k-point scan): one pass that
+            // counts into a 64-slot open-addressing table in local memory — O(cnt) while the cell holds at most 48 distinct
+            // labels (semantic classes); a cell with more falls back to the quadratic count.
             const int l = ch - 3 - fdim;
             int best = 0, best_n = 0;
-            for (int s = s0; s < s1; ++s) {
-                const int v = labels[(size_t)order[s] * ldim + l];
-                int n = 0;
-                for (int t = s0; t < s1; ++t) n += labels[(size_t)order[t] * ldim + l] == v ? 1 : 0;
-                if (n > best_n || (n == best_n && v < best)) { best = v; best_n = n; }
+            bool done = false;
+            if (cnt > 64) {
+                int hk[64], hc[64];
+                for (int q = 0; q < 64; ++q) hc[q] = 0;
+                int distinct = 0;
+                bool overflow = false;
+                for (int s = s0; s < s1 && !overflow; ++s) {
+                    const int v = labels[(size_t)order[s] * ldim + l];
+                    unsigned h = ((unsigned)v * 2654435761u) >> 26;
+                    while (hc[h] != 0 && hk[h] != v) h = (h + 1) & 63;
+                    if (hc[h] == 0) { if (++distinct > 48) { overflow = true; break; } hk[h] = v; }
+                    ++hc[h];
+                }
+                if (!overflow) {
+                    for (int q = 0; q < 64; ++q)
+                        if (hc[q] > best_n || (hc[q] == best_n && hc[q] > 0 && hk[q] < best)) { best = hk[q]; best_n = hc[q]; }
+                    done = true;
+                }
+            }
+            if (!done) {
+                best = 0; best_n = 0;
+                for (int s = s0; s < s1; ++s) {
+                    const int v = labels[(size_t)order[s] * ldim + l];
+                    int n = 0;
+                    for (int t = s0; t < s1; ++t) n += labels[(size_t)order[t] * ldim + l] == v ? 1 : 0;
+                    if (n > best_n || (n == best_n && v < best)) { best = v; best_n = n; }
+                }
             }
             out_labels[(size_t)cell * ldim + l] = best;
         }

@@ -925,21 +925,18 @@ extern "C" int ri_mutual_nn_tf32x3(const float* desc1, const float* desc2, int P
 
     {
         const size_t smem = (size_t)kStages * kStageBytes + sizeof(GemmSmem) + 1024;
-        cudaError_t e = cudaFuncSetAttribute(match_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
+        const RiEnv& env = ri_env();
         const int tiles_m = (n1 + kTileM - 1) / kTileM, tiles_n = L.n2p / kTileN;
         const long long total = (long long)P * tiles_m * tiles_n;
         if (total > 0x7fffffffLL) return RI_ERR_UNSUPPORTED;
         const int grid = total < ri_num_sms() ? (int)total : ri_num_sms();
-        unsigned long long* dbg = reinterpret_cast<unsigned long long*>(getenv("RI_MATCH_DBG") ? ws + L.mutual : nullptr);
+        unsigned long long* dbg = reinterpret_cast<unsigned long long*>(env.match_dbg ? ws + L.mutual : nullptr);
         // default: CTA pairs (cta_group::2) when a pair tile is not mostly padding; RI_MATCH_PAIR=0 / 1 forces a form
-        const char* pev = getenv("RI_MATCH_PAIR");
-        const bool pair_form = pev ? atoi(pev) == 1 : (n1 > kTileM && ri_num_sms() >= 2);
+        const bool pair_form = env.match_pair >= 0 ? env.match_pair == 1 : (n1 > kTileM && ri_num_sms() >= 2);
         if (pair_form) {
             // CTA pairs over 256 x 256 tiles (cta_group::2)
             const size_t smem2 = (size_t)kStagesP * kStage2Bytes + sizeof(GemmSmem) + 1024;
-            e = cudaFuncSetAttribute(match_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-            if (e != cudaSuccess) return (int)e;
+            RI_KERNEL_SETUP(match_gemm_pair_kernel, true, -1);
             const int ptiles_m = (n1 + kPairTileM - 1) / kPairTileM;
             const long long ptotal = (long long)P * ptiles_m * tiles_n;
             int clusters = ri_num_sms() / 2;
@@ -947,11 +944,12 @@ extern "C" int ri_mutual_nn_tf32x3(const float* desc1, const float* desc2, int P
             match_gemm_pair_kernel<<<2 * clusters, kPThreadsP, smem2, st>>>(img1, img2, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp,
                                                                           ptiles_m, tiles_n, (int)ptotal, rowkey, colkey, dbg);
         } else {
+            RI_KERNEL_SETUP(match_gemm_kernel, true, -1);
             match_gemm_kernel<<<grid, kPThreads, smem, st>>>(img1, img2, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp, tiles_m, tiles_n,
                                                              (int)total, rowkey, colkey, dbg);
         }
         RI_LAUNCH_CHECK();
-        if (getenv("RI_MATCH_DBG")) return RI_OK;            // debug: keep the stamps (match_dist would overwrite them)
+        if (env.match_dbg) return RI_OK;                     // debug: keep the stamps (match_dist would overwrite them)
     }
     int* mutual = reinterpret_cast<int*>(ws + L.mutual);
     match_dist_kernel<<<dim3((n1 + kDistRows - 1) / kDistRows, P), kDistThreads, 0, st>>>(

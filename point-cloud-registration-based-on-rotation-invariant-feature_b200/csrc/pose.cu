@@ -387,12 +387,8 @@ extern "C" int ri_pose_from_matches_f32(const float* src, const float* tgt, cons
     const int cap = ld < kMaxMatches ? ld : kMaxMatches;
     const size_t smem = (size_t)cap * 2 * sizeof(float3);
     cudaError_t e;
-    if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(pose_ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(pose_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
+    RI_KERNEL_SETUP(pose_ransac_kernel, true, -1);
+    RI_KERNEL_SETUP(pose_refine_kernel, true, -1);
     if (hyps > 0) {
         if (best == nullptr) return RI_ERR_WORKSPACE;
         e = cudaMemsetAsync(best, 0, (size_t)P * sizeof(unsigned long long), st);

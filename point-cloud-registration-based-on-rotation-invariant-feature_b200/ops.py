@@ -35,16 +35,27 @@ def _same_device(*ts):
     return d
 
 
+def _shape(t, name, *want):
+    """Raise (before anything is enqueued) unless t has exactly the dimensions `want` (None = any size)."""
+    if t.dim() != len(want) or any(w is not None and int(d) != int(w) for d, w in zip(t.shape, want)):
+        raise RuntimeError("%s must have shape [%s], got %s" % (name, ", ".join("*" if w is None else str(w) for w in want),
+                                                               list(t.shape)))
+
+
 _WS = {}
+_WS_MAX = 8        # scratch buffers kept alive: (device, stream) pairs come and go, the cache must not grow with them
 
 
 def _workspace(device, nbytes):
-    """Per-(device, stream) scratch buffer for the voxelizer (stream-ordered reuse is safe on one stream)."""
+    """Per-(device, stream) scratch buffer for the voxelizer (stream-ordered reuse is safe on one stream).  The cache holds
+    the _WS_MAX most recently used buffers; an evicted buffer is freed by the caching allocator in stream order."""
     key = (device, _stream())
-    buf = _WS.get(key)
+    buf = _WS.pop(key, None)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
-        _WS[key] = buf
+    _WS[key] = buf                                   # re-inserted last: dicts keep insertion order
+    while len(_WS) > _WS_MAX:
+        _WS.pop(next(iter(_WS)))
     return buf
 
 
@@ -199,7 +210,10 @@ def ppf(coords: torch.Tensor, center: torch.Tensor, normals: torch.Tensor, cente
     for t, nm in ((coords, "coords"), (center, "center"), (normals, "normals"), (center_normal, "center_normal")):
         _req(t, nm, torch.float32)
     dev = _same_device(coords, center, normals, center_normal)
+    _shape(coords, "coords", None, 3, None)
     B, _, L = coords.shape
+    for t, nm in ((center, "center"), (normals, "normals"), (center_normal, "center_normal")):
+        _shape(t, nm, B, 3, L)
     with torch.cuda.device(dev):
         feat = torch.empty((B, 4, L), dtype=torch.float32, device=dev)
         _check(_L.ri_ppf_f32(coords.data_ptr(), center.data_ptr(), normals.data_ptr(), center_normal.data_ptr(),
@@ -217,7 +231,9 @@ def _(coords, center, normals, center_normal):
 def ppf_gather(xyz: torch.Tensor, normals: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     _req(xyz, "xyz", torch.float32); _req(normals, "normals", torch.float32); _req(idx, "idx", torch.int32)
     dev = _same_device(xyz, normals, idx)
+    _shape(xyz, "xyz", None, 3, None)
     B, _, N = xyz.shape
+    _shape(normals, "normals", B, 3, N); _shape(idx, "idx", B, None, N)
     k = idx.shape[1]
     with torch.cuda.device(dev):
         out = torch.empty((B, 4, k, N), dtype=torch.float32, device=dev)
@@ -236,7 +252,11 @@ def _(xyz, normals, idx):
 def _voxelize(fn, what, features, coords, r, coord_dtype):
     _req(features, "features", torch.float32); _req(coords, "coords", coord_dtype)
     dev = _same_device(features, coords)
+    _shape(features, "features", None, None, None)
     B, C, N = features.shape
+    _shape(coords, "coords", B, 3, N)
+    if r <= 0:
+        raise RuntimeError("resolution must be positive")
     s = r * r * r
     with torch.cuda.device(dev):
         out = torch.empty((B, C, s), dtype=torch.float32, device=dev)
@@ -262,7 +282,11 @@ def cube_voxelize(features: torch.Tensor, coords: torch.Tensor, r: int) -> tuple
 def _voxelize_edge(fn, what, features, coords, r, coord_dtype):
     _req(features, "features", torch.float32); _req(coords, "coords", coord_dtype)
     dev = _same_device(features, coords)
+    _shape(features, "features", None, None, None)
     B, C, N = features.shape
+    _shape(coords, "coords", B, 3, N)
+    if r <= 0:
+        raise RuntimeError("resolution must be positive")
     s = r * r * r
     with torch.cuda.device(dev):
         out = torch.empty((B, C, s), dtype=torch.float32, device=dev)
@@ -331,8 +355,9 @@ def trilinear_devox(coords: torch.Tensor, features: torch.Tensor, r: int) -> tup
     _req(features, "features", torch.float32); _req(coords, "coords", torch.float32)
     dev = _same_device(features, coords)
     B, C = features.shape[:2]
+    _shape(coords, "coords", B, 3, None)
     N = coords.shape[2]
-    if features.numel() != B * C * r ** 3:
+    if r <= 0 or features.numel() != B * C * r ** 3:
         raise RuntimeError("features must hold B*C*r^3 elements")
     with torch.cuda.device(dev):
         outs = torch.empty((B, C, N), dtype=torch.float32, device=dev)
@@ -348,8 +373,10 @@ def sph_trilinear_devox(coords: torch.Tensor, features: torch.Tensor, g_inds: to
     _req(features, "features", torch.float32); _req(coords, "coords", torch.float32); _req(g_inds, "g_inds", torch.int32)
     dev = _same_device(features, coords, g_inds)
     B, C = features.shape[:2]
+    _shape(coords, "coords", B, 3, None)
     N = coords.shape[2]
-    if features.numel() != B * C * r ** 3:
+    _shape(g_inds, "g_inds", B, N)
+    if r <= 0 or features.numel() != B * C * r ** 3:
         raise RuntimeError("features must hold B*C*r^3 elements")
     with torch.cuda.device(dev):
         outs = torch.empty((B, C, N), dtype=torch.float32, device=dev)
@@ -445,8 +472,12 @@ def _(xyz, normals, k):
 def ball_query(centers_coords: torch.Tensor, points_coords: torch.Tensor, radius: float, num_neighbors: int) -> torch.Tensor:
     _req(centers_coords, "centers_coords", torch.float32); _req(points_coords, "points_coords", torch.float32)
     dev = _same_device(centers_coords, points_coords)
+    _shape(centers_coords, "centers_coords", None, 3, None)
     B, _, M = centers_coords.shape
+    _shape(points_coords, "points_coords", B, 3, None)
     N = points_coords.shape[2]
+    if num_neighbors <= 0:
+        raise RuntimeError("num_neighbors must be positive")
     with torch.cuda.device(dev):
         out = torch.empty((B, M, num_neighbors), dtype=torch.int32, device=dev)
         _check(_L.ri_ball_query_f32(centers_coords.data_ptr(), points_coords.data_ptr(), B, N, M, float(radius),
@@ -463,7 +494,9 @@ def _(centers_coords, points_coords, radius, num_neighbors):
 def grouping(features: torch.Tensor, indices: torch.Tensor) -> torch.Tensor:
     _req(features, "features", torch.float32); _req(indices, "indices", torch.int32)
     dev = _same_device(features, indices)
+    _shape(features, "features", None, None, None)
     B, C, N = features.shape
+    _shape(indices, "indices", B, None, None)
     _, M, U = indices.shape
     with torch.cuda.device(dev):
         out = torch.empty((B, C, M, U), dtype=torch.float32, device=dev)
@@ -481,7 +514,9 @@ def _(features, indices):
 def grouping_backward(grad_y: torch.Tensor, indices: torch.Tensor, n: int) -> torch.Tensor:
     _req(grad_y, "grad_y", torch.float32); _req(indices, "indices", torch.int32)
     dev = _same_device(grad_y, indices)
+    _shape(grad_y, "grad_y", None, None, None, None)
     B, C, M, U = grad_y.shape
+    _shape(indices, "indices", B, M, U)
     with torch.cuda.device(dev):
         gx = torch.empty((B, C, n), dtype=torch.float32, device=dev)
         _check(_L.ri_grouping_backward_f32(grad_y.data_ptr(), indices.data_ptr(), B, C, n, M, U, gx.data_ptr(), _stream()),
@@ -648,8 +683,11 @@ def local_ppf(points_coords: torch.Tensor, points_normals: torch.Tensor, centers
         _req(t, n, torch.float32)
     _req(neighbors, "neighbors", torch.int32)
     dev = _same_device(points_coords, points_normals, centers_coords, centers_normals, neighbors)
+    _shape(points_coords, "points_coords", None, 3, None)
     B, _, N = points_coords.shape
+    _shape(points_normals, "points_normals", B, 3, N); _shape(centers_coords, "centers_coords", B, 3, None)
     M = centers_coords.shape[2]
+    _shape(centers_normals, "centers_normals", B, 3, M); _shape(neighbors, "neighbors", B, M, None)
     U = neighbors.shape[2]
     with torch.cuda.device(dev):
         out = torch.empty((B, 4, U, M), dtype=torch.float32, device=dev)

@@ -111,3 +111,24 @@ def test_cuda_scan_sized_and_tensor_api(oracle):
     # empty cloud
     e = ri_b200.grid_sub_sampling(torch.empty((0, 3), device="cuda"), grid_size=0.1)
     assert e.shape == (0, 3)
+
+
+@pytest.mark.gpu
+def test_cuda_labels_in_large_cells(oracle):
+    """A coarse grid on a scan: hundreds to thousands of points per cell — the label vote must stay linear in the cell size
+    (it used to recount the whole cell for every point) and still name the most frequent label, smallest on ties.  One label
+    column has more distinct values per cell than the kernel's counting table holds: that column takes the quadratic path."""
+    import time
+    import torch
+    import ri_b200
+    from ri_b200 import synth
+    rng = np.random.default_rng(12)
+    N = 60000
+    pts = np.ascontiguousarray(synth.make_scan(N, seed=9)[:3].T)
+    labels = np.stack([rng.integers(0, 13, N), rng.integers(0, 3, N), rng.integers(0, 500, N)], 1).astype(np.int32)
+    torch.cuda.synchronize(); t0 = time.time()
+    sub_p, sub_l = ri_b200.grid_sub_sampling(torch.from_numpy(pts).cuda(), labels=torch.from_numpy(labels).cuda(), grid_size=0.6)
+    torch.cuda.synchronize(); took = time.time() - t0
+    op, _, ol, _ = oracle.grid_subsample(pts, None, labels, 0.6)
+    assert np.array_equal(sub_p.cpu().numpy(), op) and np.array_equal(sub_l.cpu().numpy(), ol)
+    assert sub_p.shape[0] < 400 and took < 2.0
