@@ -40,6 +40,11 @@ int ri_abi_version(void);
 /* Debug aid: a one-thread kernel that stores the device's nanosecond timer (%globaltimer) into *slot. */
 int ri_debug_stamp(unsigned long long* slot, void* stream);
 
+/* Debug aid for tests and tools: the environment knobs of DESIGN.md §11 are read once per process; this sets one of them
+ * afterwards, by its variable name (e.g. "RI_DEVOX_STREAM", -1 = unset).  Not to be called while launches are in flight on
+ * other threads.  RI_ERR_BAD_ARG for a name that cannot be changed at run time. */
+int ri_debug_set_knob(const char* name, int value);
+
 /* ---- k-nearest neighbours -------------------------------------------------------------------------------
  * One direction of knn_forward_cuda (knn/knn.cpp:6-25 -> KnnKernel knn/knn.cu:5-49): for each of the n points of
  * xyz1 [B,c,n] its k nearest (squared L2) among the m points of xyz2 [B,c,m].

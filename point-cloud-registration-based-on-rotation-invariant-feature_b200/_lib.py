@@ -14,6 +14,7 @@ _Z = ctypes.c_size_t
 SIGNATURES = {
     "ri_abi_version": (_I, []),
     "ri_debug_stamp": (_I, [_P, _P]),
+    "ri_debug_set_knob": (_I, [ctypes.c_char_p, _I]),
     "ri_knn_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ri_knn_thread_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ri_knn_bilateral_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),

@@ -355,6 +355,227 @@ static int sd_launch(const SdPlan& pl, const float* coords, const float* feat, i
     return RI_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sector-compacting devoxelizer (both grids; N <= 1024 points per cloud).  What the 8 corners of a cloud's points touch
+// is a SMALL part of a channel plane and it is the same part in every plane: measured on the bench clouds
+// (tools/exp_devox_sectors.py) 26.5 % of the 32-byte sectors of a plane on the cube grid at r = 32 (8 % at r = 64), 0.4 % on
+// the spherical grid.  Streaming whole planes (devox_stream_kernel) reads 3.8x what is needed; gathering per point
+// (devox_kernel) asks L2 for every sector ~4 times (as many points share it) through uncoalesced 4-byte loads.  Here a CTA
+// = (cloud, group of planes):
+//   once   corner cells + weights of its points (registers); a bit per touched sector in a shared-memory bitmap, ranked by a
+//          prefix sum over the words -> the sorted list of the cloud's U distinct sectors and, per corner, its slot in it;
+//   per plane  the U sectors are copied global -> shared memory, 32 bytes each, by cp.async (every needed DRAM sector is
+//          read exactly once, as a whole, and nothing else is), double-buffered against the previous plane's arithmetic;
+//          the points then take their 8 corners from the compact buffer and run the reference's 8-term chain.
+// Same corner indices, weights and sums as devox_kernel, bit for bit.  A cloud with more distinct sectors than the buffer
+// holds (kDsCap) runs the chain on global loads instead.
+constexpr int kDsThreads = 256;
+constexpr int kDsPts = 4;                            // points per thread: N <= 1024
+constexpr int kDsCap = 3072;                         // sectors the plane buffer holds (96 KB): two planes of <= 1536, or one
+constexpr int kDsMaxWords = 2048;                    // bitmap words: r^3 / 8 sectors <= 65536
+
+template <bool SPH>
+__global__ void __launch_bounds__(kDsThreads, 2)
+devox_sectors_kernel(const float* __restrict__ coords, const float* __restrict__ feat, const int* __restrict__ g_inds,
+                     int C, int N, int r, int group, int nwords,
+                     float* __restrict__ outs, int* __restrict__ inds, float* __restrict__ wgts)
+{
+    extern __shared__ __align__(128) unsigned char ds_smem[];
+    float* buf = reinterpret_cast<float*>(ds_smem);                          // [kDsCap * 8] floats: one plane, or two halves
+    unsigned short* slist = reinterpret_cast<unsigned short*>(buf + kDsCap * 8);   // [kDsCap] sector ids, ascending
+    unsigned* bitmap = reinterpret_cast<unsigned*>(slist + kDsCap);          // [nwords]
+    int* prefix = reinterpret_cast<int*>(bitmap + nwords);                   // [nwords] sectors before this word
+    __shared__ int swarp[kDsThreads / 32];
+    __shared__ int s_total;
+
+    const int b = (int)gridDim.y - 1 - (int)blockIdx.y;                      // last-written clouds first (still in L2)
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int r2 = r * r;
+    const size_t s = (size_t)r2 * r;
+    const float* X = coords + (size_t)b * 3 * N;
+    const bool writer = blockIdx.x == 0;                                     // plane group 0 also emits inds / wgts
+
+    for (int w = tid; w < nwords; w += kDsThreads) bitmap[w] = 0u;
+    __syncthreads();
+
+    int id[kDsPts][8];
+    float wt[kDsPts][8];
+    bool defined[kDsPts];
+#pragma unroll
+    for (int q = 0; q < kDsPts; ++q) {
+        const int i = tid + q * kDsThreads;
+        defined[q] = false;
+        if (i >= N) continue;
+        defined[q] = true;
+        int first_ind = 0;
+        if (SPH) {
+            const int pos = g_inds[(size_t)b * N + i];
+            float g = 0.f, a = 0.f, be = 0.f;
+            if (pos == -1) { defined[q] = false; first_ind = -1; }
+            else if (!ri_sph_coords(X[i], X[i + N], X[i + 2 * (size_t)N], r, g, a, be)) defined[q] = false;
+            if (defined[q]) {
+                const int gg = pos / r2;
+                const int ga = (pos - gg * r2) / r;
+                const int gb = pos - gg * r2 - ga * r;
+                const float g_lo = (float)(gg / r);
+                const float a_lo = __double2float_rn(__ddiv_rn(__dmul_rn(__dmul_rn(RI_PI, 2.0), (double)ga), (double)r));
+                const float b_lo = __double2float_rn(__ddiv_rn(__dmul_rn(RI_PI, (double)gb), (double)r));
+                ri_corners(__fsub_rn(g, g_lo), __fsub_rn(a, a_lo), __fsub_rn(be, b_lo),
+                           (int)g_lo, (int)a_lo, (int)b_lo, r, r2, id[q], wt[q]);
+            }
+        } else {
+            const float x = X[i], y = X[i + N], z = X[i + 2 * (size_t)N];
+            const float xl = floorf(x), yl = floorf(y), zl = floorf(z);
+            ri_corners(__fsub_rn(x, xl), __fsub_rn(y, yl), __fsub_rn(z, zl), (int)xl, (int)yl, (int)zl, r, r2, id[q], wt[q]);
+        }
+        if (writer) {
+            int* I = inds + (size_t)b * 8 * N + i;
+            float* Wt = wgts + (size_t)b * 8 * N + i;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                I[(size_t)c * N] = defined[q] ? id[q][c] : (c == 0 ? first_ind : 0);
+                Wt[(size_t)c * N] = defined[q] ? wt[q][c] : 0.f;
+            }
+        }
+        if (defined[q]) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) atomicOr(&bitmap[id[q][c] >> 8], 1u << ((id[q][c] >> 3) & 31));
+        }
+    }
+    __syncthreads();
+    // ---- rank the touched sectors: exclusive prefix sum of the words' popcounts
+    {
+        const int per = (nwords + kDsThreads - 1) / kDsThreads;              // consecutive words per thread
+        const int w0 = tid * per, w1 = min(nwords, w0 + per);
+        int sum = 0;
+        for (int w = w0; w < w1; ++w) sum += __popc(bitmap[w]);
+        int inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) swarp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            const int v = lane < kDsThreads / 32 ? swarp[lane] : 0;
+            int wi = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            if (lane < kDsThreads / 32) swarp[lane] = wi - v;
+            if (lane == kDsThreads / 32 - 1) s_total = wi;
+        }
+        __syncthreads();
+        int run = swarp[wid] + inc - sum;
+        for (int w = w0; w < w1; ++w) { prefix[w] = run; run += __popc(bitmap[w]); }
+    }
+    __syncthreads();
+    const int U = s_total;
+    const bool compact = U <= kDsCap;
+    // ---- the sorted sector list, and every corner's float offset in a plane buffer
+    unsigned short off[kDsPts][8];
+    if (compact) {
+        for (int w = tid; w < nwords; w += kDsThreads) {
+            unsigned m = bitmap[w];
+            int k2 = prefix[w];
+            while (m) { const int bit = __ffs(m) - 1; m &= m - 1; slist[k2++] = (unsigned short)(w * 32 + bit); }
+        }
+#pragma unroll
+        for (int q = 0; q < kDsPts; ++q) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                off[q][c] = 0;
+                if (defined[q]) {
+                    const int sec = id[q][c] >> 3, w = sec >> 5;
+                    const int slot = prefix[w] + __popc(bitmap[w] & ((1u << (sec & 31)) - 1u));
+                    off[q][c] = (unsigned short)(slot * 8 + (id[q][c] & 7));
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const int c0 = blockIdx.x * group, c1 = min(C, c0 + group);
+    const float* F = feat + (size_t)b * C * s;
+    float* O = outs + (size_t)b * C * N;
+    auto fetch = [&](int c, float* dst) {                                    // the cloud's sectors of plane c -> dst
+        const float* src = F + (size_t)c * s;
+        for (int j = tid; j < 2 * U; j += kDsThreads) {                      // two 16-byte halves per sector
+            const int sec = slist[j >> 1], h = j & 1;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                         :: "r"(ri_smem_u32(dst + (j >> 1) * 8 + h * 4)), "l"(src + (size_t)sec * 8 + h * 4) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (compact) {
+        // a cloud whose sectors fill at most half of the buffer runs two planes deep (the next plane's copies fly under this
+        // plane's arithmetic); a larger one plane at a time (the other CTA of the SM fills the gaps)
+        const int nbuf = U <= kDsCap / 2 ? 2 : 1;
+        const int half = kDsCap / 2 * 8;
+        if (nbuf == 2 && c0 < c1) fetch(c0, buf);
+        for (int c = c0; c < c1; ++c) {
+            float* cur = buf + (nbuf == 2 ? ((c - c0) & 1) * half : 0);
+            if (nbuf == 2) {
+                if (c + 1 < c1) { fetch(c + 1, buf + ((c + 1 - c0) & 1) * half); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+                else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            } else {
+                fetch(c, cur);
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < kDsPts; ++q) {
+                const int i = tid + q * kDsThreads;
+                if (i >= N) continue;
+                float acc = 0.f;                                             // the reference leaves its zero-fill for undefined points
+                if (defined[q]) {
+                    acc = __fmul_rn(wt[q][1], cur[off[q][1]]);
+                    acc = __fmaf_rn(wt[q][0], cur[off[q][0]], acc);
+                    acc = __fmaf_rn(wt[q][2], cur[off[q][2]], acc);
+                    acc = __fmaf_rn(wt[q][3], cur[off[q][3]], acc);
+                    acc = __fmaf_rn(wt[q][4], cur[off[q][4]], acc);
+                    acc = __fmaf_rn(wt[q][5], cur[off[q][5]], acc);
+                    acc = __fmaf_rn(wt[q][6], cur[off[q][6]], acc);
+                    acc = __fmaf_rn(wt[q][7], cur[off[q][7]], acc);
+                }
+                O[(size_t)c * N + i] = acc;
+            }
+            __syncthreads();                                                 // `cur` is refilled next
+        }
+    } else {
+        for (int c = c0; c < c1; ++c) {
+#pragma unroll
+            for (int q = 0; q < kDsPts; ++q) {
+                const int i = tid + q * kDsThreads;
+                if (i >= N) continue;
+                O[(size_t)c * N + i] = defined[q] ? devox_sum(F + (size_t)c * s, id[q], wt[q]) : 0.f;
+            }
+        }
+    }
+}
+
+template <bool SPH>
+static int ds_launch(const float* coords, const float* feat, const int* g_inds, int B, int C, int N, int r,
+                     float* outs, int* inds, float* wgts, cudaStream_t st)
+{
+    const long long s = (long long)r * r * r;
+    const int nwords = (int)((s / 8 + 31) / 32);
+    // planes per CTA: enough CTAs for two per SM, at least 4 planes each so the per-cloud setup is amortised
+    int group = (int)(((long long)B * C + 2LL * ri_num_sms() - 1) / (2LL * ri_num_sms()));
+    if (group < 4) group = 4;
+    if (group > C) group = C > 0 ? C : 1;
+    const int groups = C > 0 ? (C + group - 1) / group : 1;
+    const size_t smem = (size_t)kDsCap * 32 + (size_t)kDsCap * 2 + (size_t)nwords * 8;
+    auto kern = devox_sectors_kernel<SPH>;
+    RI_KERNEL_SETUP(kern, true, ri_step_carveout_percent());
+    kern<<<dim3(groups, B), kDsThreads, smem, st>>>(coords, feat, g_inds, C, N, r, group, nwords, outs, inds, wgts);
+    RI_LAUNCH_CHECK();
+    return RI_OK;
+}
+
 // out[b, c, i]     = inds[b,i] == -1 ? 0 : feat[b,c,i] - avg[b,c,inds[b,i]]
 // out[b, C + c, i] = feat[b,c,i]                                                    (pvconv.py:68-90)
 constexpr int kEdgeThreads = 128;
@@ -396,6 +617,16 @@ int devox_impl(const float* coords, const float* feat, const int* g_inds, int B,
     if (B < 0 || C < 0 || N < 0 || r <= 0 || r > 1024) return RI_ERR_BAD_ARG;
     if ((long long)r * r * r > 0x7fffffffLL || B > 65535) return RI_ERR_UNSUPPORTED;
     if (B == 0 || N == 0) return RI_OK;
+    {
+        // sector-compacting form: N <= 1024 points, r^3 a multiple of 8 with at most 65536 sectors per plane, 32-byte
+        // aligned planes.  RI_DEVOX_STREAM = 0 / 1 still forces the gather / streaming forms (tests, experiments).
+        const long long s = (long long)r * r * r;
+        // (the spherical grid keeps the per-point gather form: its index quirks fold a cloud's corners onto ~17 sectors of a
+        // plane, there is nothing to compact — 21 us against 27)
+        if (!SPH && ri_env().devox_stream < 0 && N <= kDsThreads * kDsPts && s % 8 == 0 && s / 8 <= 32LL * kDsMaxWords &&
+            ((uintptr_t)feat & 31) == 0)
+            return ds_launch<SPH>(coords, feat, g_inds, B, C, N, r, outs, inds, wgts, st);
+    }
     if (!SPH) {
         SdPlan pl;
         if ((long long)B * C < 0x7fffffffLL && sd_plan(feat, C, N, r, pl)) {

@@ -46,38 +46,9 @@ struct RiEnv {
     int match_dbg;                          // RI_MATCH_DBG          GEMM only, %globaltimer stamps in the workspace
     int fill_form;                          // RI_FILL_FORM          -1 unset, 0 CTA-synchronous writer, 1 warp-autonomous writer
 };
-static inline int ri_env_int(const char* name, int unset)
-{
-    const char* ev = getenv(name);
-    return ev ? atoi(ev) : unset;
-}
-static inline const RiEnv& ri_env()
-{
-    static const RiEnv env = [] {
-        RiEnv e;
-        e.carveout_pct = ri_env_int("RI_CARVEOUT_PCT", 100);
-        if (e.carveout_pct < 1 || e.carveout_pct > 100) e.carveout_pct = 100;
-        e.devox_stream = ri_env_int("RI_DEVOX_STREAM", -1);
-        e.devox_tile_kb = ri_env_int("RI_DEVOX_TILE_KB", -1);
-        e.devox_ring_kb = ri_env_int("RI_DEVOX_RING_KB", -1);
-        e.devox_pad_kb = ri_env_int("RI_DEVOX_PAD_KB", -1);
-        e.devox_dbg_skip = getenv("RI_DEVOX_DBG_SKIP") != nullptr;
-        e.fill_ring = ri_env_int("RI_FILL_RING", -1);
-        e.fill_ctas = ri_env_int("RI_FILL_CTAS", -1);
-        e.fill_pad_kb = ri_env_int("RI_FILL_PAD_KB", -1);
-        e.fill_group = ri_env_int("RI_FILL_GROUP", -1);
-        e.fill_warps = ri_env_int("RI_FILL_WARPS", -1);
-        e.fill_listcap = ri_env_int("RI_FILL_LISTCAP", -1);
-        e.fill_tile_cells = ri_env_int("RI_FILL_TILE", -1);
-        e.vox_atomic = getenv("RI_VOX_ATOMIC") != nullptr;
-        e.ppf_maxl1 = ri_env_int("RI_PPF_MAXL1", 0) == 1;
-        e.match_pair = ri_env_int("RI_MATCH_PAIR", -1);
-        e.match_dbg = getenv("RI_MATCH_DBG") != nullptr;
-        e.fill_form = ri_env_int("RI_FILL_FORM", -1);
-        return e;
-    }();
-    return env;
-}
+// One instance per process, defined in abi.cu; initialised on first use (thread-safe), read-only on every launch path.
+// ri_debug_set_knob() (tests, tools) overwrites a field — not while launches are in flight on other threads.
+const RiEnv& ri_env();
 
 // SM count of the CURRENT device, cached per device ordinal.
 static inline int ri_num_sms()

@@ -54,7 +54,9 @@ def test_ctypes_table_matches_header(built_lib):
         assert len(argtypes) == len(args), name
         assert (res is ctypes.c_size_t) == (ret == "size_t"), name
         for a, t in zip(args, argtypes):
-            if "*" in a:
+            if a.startswith("const char*"):
+                assert t is ctypes.c_char_p, (name, a)
+            elif "*" in a:
                 assert t is ctypes.c_void_p, (name, a)
             elif a.startswith("size_t"):
                 assert t is ctypes.c_size_t, (name, a)

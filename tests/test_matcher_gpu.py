@@ -192,17 +192,14 @@ def test_pair_and_single_cta_forms_agree(P, C, n1, n2, pm):
     shape1, shape2 = ((P, n1, C), (P, n2, C)) if pm else ((P, C, n1), (P, C, n2))
     d1 = torch.randn(shape1, device="cuda", generator=g); d2 = torch.randn(shape2, device="cuda", generator=g)
     res = {}
-    prev = os.environ.get("RI_MATCH_PAIR")
+    L = ri_b200._lib.lib
     try:
         for mode in ("0", "1"):
-            os.environ["RI_MATCH_PAIR"] = mode
+            assert L.ri_debug_set_knob(b"RI_MATCH_PAIR", int(mode)) == 0
             r = ri_b200.matcher.mutual_nn(d1, d2, point_major=pm)
             torch.cuda.synchronize()
             res[mode] = {k: v.clone() for k, v in r.items()}
     finally:
-        if prev is None:
-            os.environ.pop("RI_MATCH_PAIR", None)
-        else:
-            os.environ["RI_MATCH_PAIR"] = prev
+        L.ri_debug_set_knob(b"RI_MATCH_PAIR", -1)
     for k in res["0"]:
         assert torch.equal(res["0"][k], res["1"][k]), k

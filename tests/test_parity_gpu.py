@@ -233,8 +233,8 @@ def test_sph_voxelize_vs_reference(ri, ref_backend, oracle, B, N, C, r):
 @pytest.mark.parametrize("B,N,C,r", [(32, 1024, 71, 32), (3, 1000, 5, 16), (2, 2048, 3, 32), (2, 1500, 4, 32), (5, 257, 2, 8),
                                       (1, 64, 150, 32), (2, 300, 3, 2), (2, 1024, 3, 64), (3, 1024, 7, 22)])
 def test_cube_devox_streaming_vs_gather_vs_oracle(ri, oracle, B, N, C, r):
-    """The two forms of the cube devoxelizer (TMA-streamed planes + shared-memory gathers; per-thread global gathers) and the C
-    oracle agree bit for bit on outs / inds / wgts — including points on cell boundaries, on the far faces (x = r-1: no
+    """The three forms of the cube devoxelizer (per-thread global gathers; TMA-streamed planes + shared-memory gathers; the
+    default — the cloud's touched 32-byte sectors compacted into shared memory, where it applies) and the C oracle agree bit for bit on outs / inds / wgts — including points on cell boundaries, on the far faces (x = r-1: no
     high corner) and at the grid's corners."""
     import os
     g = torch.Generator().manual_seed(100 + r + N)
@@ -245,19 +245,16 @@ def test_cube_devox_streaming_vs_gather_vs_oracle(ri, oracle, B, N, C, r):
     nc = nc.cuda().contiguous()
     grid = torch.randn(B, C, r, r, r, generator=g).cuda()
     res = {}
-    prev = os.environ.get("RI_DEVOX_STREAM")
+    L = ri._lib.lib
     try:
-        for mode in ("0", "1"):
-            os.environ["RI_DEVOX_STREAM"] = mode
+        for mode in ("0", "1", "sectors"):
+            assert L.ri_debug_set_knob(b"RI_DEVOX_STREAM", -1 if mode == "sectors" else int(mode)) == 0
             res[mode] = torch.ops.ri.trilinear_devox(nc, grid, r)
             torch.cuda.synchronize()
     finally:
-        if prev is None:
-            os.environ.pop("RI_DEVOX_STREAM", None)
-        else:
-            os.environ["RI_DEVOX_STREAM"] = prev
+        L.ri_debug_set_knob(b"RI_DEVOX_STREAM", -1)
     oo, oi, ow = oracle.trilinear_devoxelize(A(nc), A(grid), r)
-    for mode in ("0", "1"):
+    for mode in ("0", "1", "sectors"):
         o, di, dw = res[mode]
         assert np.array_equal(A(di), oi), "corner indices, form %s" % mode
         assert np.array_equal(A(dw), ow), "corner weights, form %s" % mode

@@ -16,7 +16,7 @@ def run(i):
     nc, g, o, di, dw = bufs[i % 3]
     assert L.ri_trilinear_devox_f32(nc.data_ptr(), g.data_ptr(), B, C, N, r, o.data_ptr(), di.data_ptr(), dw.data_ptr(), st) == 0
 for mode in (None, "1"):
-    if mode: os.environ["RI_DEVOX_DBG_SKIP"] = mode
+    if mode: os.environ["RI_DEVOX_DBG_SKIP"] = mode    # read once per process: run one mode per process
     for i in range(6): run(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
