@@ -223,15 +223,20 @@ def measure_workload(key, args, ri_b200, H, rank, world, local, headline):
     gathered = [torch.empty((world * B, N), dtype=torch.int32, device=dev) for _ in range(RING)] if world > 1 else None
     gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
 
+    gather_done = [torch.cuda.Event() for _ in range(RING)] if world > 1 else None
+
     def lane_steps(n):
         lanes.begin()
         for i in range(n):
+            q = i % RING
+            if world > 1 and i >= RING:              # engine q's outputs are rewritten: its previous gather must have read them
+                lanes.streams[i % lanes.lanes].wait_event(gather_done[q])
             lanes.forward(i)
             if world > 1:
-                q = i % RING
                 gather_stream.wait_event(lanes._done[q])
                 with torch.cuda.stream(gather_stream):
                     torch.distributed.all_gather_into_tensor(gathered[q], engines[q].ind)
+                    gather_done[q].record(gather_stream)
         lanes.end()
         if world > 1:
             torch.cuda.current_stream().wait_stream(gather_stream)
