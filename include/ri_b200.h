@@ -209,6 +209,16 @@ int ri_local_ppf_f32(const float* points_coords, const float* points_normals, co
                      const float* centers_normals, const int* neighbors, int B, int N, int M, int U,
                      float* out, void* stream);
 
+/* The whole local-feature branch of the shipped models (pvcnn_classify.py:61-67, 252-271) from the ball-query indices:
+ * local point-pair features -> SharedMLP(4 -> 32 -> 64) in eval mode -> max over the neighbours, in one kernel (layer 2 on
+ * tcgen05 as a 3xTF32 split product; nothing between the indices and the result leaves the SM).  w1 [32,4], b1 [32],
+ * w2 [64,32], b2 [64]: the two 1x1 convolutions with their BatchNorm (running statistics) folded in.  neighbors [B,M,U];
+ * out [B,64,M].  U == 128, C1 == 32, C2 == 64 (the shipped shape), else RI_ERR_UNSUPPORTED. */
+int ri_local_ppf_mlp_max_f32(const float* points_coords, const float* points_normals, const float* centers_coords,
+                             const float* centers_normals, const int* neighbors, int B, int N, int M, int U,
+                             const float* w1, const float* b1, int C1, const float* w2, const float* b2, int C2,
+                             float* out, void* stream);
+
 /* grouping_forward / grouping_backward (grouping/grouping.cu:18-44, 58-84): out [B,C,M,U] = feat[b, c, idx[b, m, u]];
  * grad_x [B,C,N] += grad_y scattered through idx (float atomics, as the reference; grad_x is zeroed first). */
 int ri_grouping_f32(const float* feat, const int* idx, int B, int C, int N, int M, int U, float* out, void* stream);

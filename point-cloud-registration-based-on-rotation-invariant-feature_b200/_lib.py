@@ -44,6 +44,7 @@ SIGNATURES = {
     "ri_voxel_edge_gather_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "ri_ball_query_f32": (_I, [_P, _P, _I, _I, _I, ctypes.c_float, _I, _P, _P]),
     "ri_local_ppf_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "ri_local_ppf_mlp_max_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P]),
     "ri_grouping_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "ri_grouping_backward_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "ri_grid_subsample_workspace_bytes": (_Z, [_I]),

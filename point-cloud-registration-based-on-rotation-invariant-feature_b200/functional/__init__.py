@@ -6,5 +6,5 @@ from .voxelization import avg_voxelize, spherical_avg_voxelize, avg_voxelize_edg
 from .ppf import ppf, knn_ppf, knn_ppf_fused
 from .knn import k_nearest_neighbor, knn_indices
 from .edge import voxel_edge_features
-from .ball_query import ball_query, grouping, local_ppf, ball_local_ppf
+from .ball_query import ball_query, grouping, local_ppf, ball_local_ppf, fold_fuser, local_ppf_features
 from .lrf import change_coords, global_ppf

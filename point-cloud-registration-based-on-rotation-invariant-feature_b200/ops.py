@@ -700,3 +700,37 @@ def local_ppf(points_coords: torch.Tensor, points_normals: torch.Tensor, centers
 @local_ppf.register_fake
 def _(points_coords, points_normals, centers_coords, centers_normals, neighbors):
     return points_coords.new_empty((points_coords.shape[0], 4, neighbors.shape[2], centers_coords.shape[2]))
+
+
+@torch.library.custom_op("ri::local_ppf_mlp_max", mutates_args=())
+def local_ppf_mlp_max(points_coords: torch.Tensor, points_normals: torch.Tensor, centers_coords: torch.Tensor,
+                      centers_normals: torch.Tensor, neighbors: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor,
+                      w2: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
+    """The local-feature branch fused (pvcnn_classify.py:252-271): points_* [B,3,N], centers_* [B,3,M], neighbors [B,M,128] i32,
+    BatchNorm-folded weights w1 [32,4], b1 [32], w2 [64,32], b2 [64] -> [B,64,M] = max over the neighbours of the two-layer MLP
+    on the local point-pair features."""
+    for t, n in ((points_coords, "points_coords"), (points_normals, "points_normals"), (centers_coords, "centers_coords"),
+                 (centers_normals, "centers_normals"), (w1, "w1"), (b1, "b1"), (w2, "w2"), (b2, "b2")):
+        _req(t, n, torch.float32)
+    _req(neighbors, "neighbors", torch.int32)
+    dev = _same_device(points_coords, points_normals, centers_coords, centers_normals, neighbors, w1, b1, w2, b2)
+    _shape(points_coords, "points_coords", None, 3, None)
+    B, _, N = points_coords.shape
+    _shape(points_normals, "points_normals", B, 3, N); _shape(centers_coords, "centers_coords", B, 3, None)
+    M = centers_coords.shape[2]
+    _shape(centers_normals, "centers_normals", B, 3, M); _shape(neighbors, "neighbors", B, M, None)
+    U = neighbors.shape[2]
+    _shape(w1, "w1", None, 4); C1 = w1.shape[0]
+    _shape(b1, "b1", C1); _shape(w2, "w2", None, C1); C2 = w2.shape[0]; _shape(b2, "b2", C2)
+    with torch.cuda.device(dev):
+        out = torch.empty((B, C2, M), dtype=torch.float32, device=dev)
+        _check(_L.ri_local_ppf_mlp_max_f32(points_coords.data_ptr(), points_normals.data_ptr(), centers_coords.data_ptr(),
+                                           centers_normals.data_ptr(), neighbors.data_ptr(), B, N, M, U,
+                                           w1.data_ptr(), b1.data_ptr(), C1, w2.data_ptr(), b2.data_ptr(), C2,
+                                           out.data_ptr(), _stream()), "ri_local_ppf_mlp_max")
+    return out
+
+
+@local_ppf_mlp_max.register_fake
+def _(points_coords, points_normals, centers_coords, centers_normals, neighbors, w1, b1, w2, b2):
+    return points_coords.new_empty((points_coords.shape[0], w2.shape[0], centers_coords.shape[2]))

@@ -121,3 +121,53 @@ def test_local_ppf_fused_equals_reference_torch_ops(oracle, B, N, U, radius):
     oedge = np.abs(np.cos(o[:, :3])) > 1 - 1e-4
     assert np.array_equal(got[:, 3].cpu().numpy(), o[:, 3])
     assert oerr[:, :3][~oedge].max() <= 2e-6
+
+
+@pytest.mark.parametrize("B,N", [(32, 1024), (3, 500), (2, 1000)])
+def test_local_feature_branch_fused_equals_torch_layers(B, N):
+    """Row f1, second half: indices -> local PPF -> SharedMLP(4 -> 32 -> 64) -> max over the 128 neighbours in ONE kernel
+    (csrc/localmlp.cu, layer 2 on tcgen05 as a 3xTF32 split product) against the reference's own sequence
+    (pvcnn_classify.py:252-271: the PPF tensor [B,4,128,N], `self.fuser(...)` = Conv2d BN ReLU Conv2d BN ReLU in eval mode,
+    `.max(dim=2).values`) evaluated by torch in fp32 with TF32 convolutions switched off.  <= 1e-5 relative to the largest
+    output (the north star's fp32 bar); the fused kernel never writes the 1 GB activation the torch path goes through."""
+    import ri_b200
+    from ri_b200 import synth
+    torch.manual_seed(5)
+    fuser = ri_b200.modules.SharedMLP(4, [32, 64], dim=2).cuda().eval()
+    with torch.no_grad():
+        for m in fuser.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0.0, 0.3); m.running_var.uniform_(0.5, 2.0)
+                m.weight.uniform_(0.5, 1.5); m.bias.normal_(0.0, 0.2)
+    pts = torch.from_numpy(synth.make_clouds(B, N, seed=41)).cuda()
+    pts[:, 3:6] = torch.nn.functional.normalize(pts[:, 3:6], dim=1)
+    xyz, nrm = pts[:, :3].contiguous(), pts[:, 3:6].contiguous()
+    ppf = ri_b200.functional.ball_local_ppf(xyz, nrm, 0.3, 128)                       # [B,4,128,N], tested above
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            want = fuser(ppf).max(dim=2).values                                        # [B,64,N]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    got = ri_b200.functional.local_ppf_features(xyz, nrm, ri_b200.functional.fold_fuser(fuser), 0.3, 128)
+    assert got.shape == want.shape == (B, 64, N)
+    finite = torch.isfinite(want)
+    assert torch.equal(torch.isfinite(got), finite)
+    scale = float(want[finite].abs().max())
+    err = float((got[finite] - want[finite]).abs().max()) / scale
+    assert err <= 1e-5, err
+    # the same weights through fp64: the fused result is as close to it as torch's fp32 layers are
+    with torch.no_grad():
+        ref64 = fuser.double()(ppf.double()).max(dim=2).values
+    e_ours = float((got.double()[finite] - ref64[finite]).abs().max()) / scale
+    e_torch = float((want.double()[finite] - ref64[finite]).abs().max()) / scale
+    assert e_ours <= max(4 * e_torch, 2e-6), (e_ours, e_torch)
+
+
+def test_local_feature_branch_rejects_other_shapes():
+    import ri_b200
+    x = torch.randn(1, 3, 64, device="cuda"); n = torch.nn.functional.normalize(torch.randn(1, 3, 64, device="cuda"), dim=1)
+    fuser = ri_b200.modules.SharedMLP(4, [32, 64], dim=2).cuda().eval()
+    with pytest.raises(RuntimeError):                                                  # 16 neighbours: not the shipped shape
+        ri_b200.functional.local_ppf_features(x, n, ri_b200.functional.fold_fuser(fuser), 0.3, 16)

@@ -54,3 +54,28 @@ def torch_block():
 c = t(lambda: ri_b200.functional.ball_local_ppf(pts, nrm, R, U))
 d = t(torch_block, 5)
 print("local PPF [B,4,U,N] incl. ball query: fused %8.1f us   BallQuery module + torch ops %8.1f us   -> %.1fx" % (c, d, d / c))
+
+# the whole local-feature branch: indices -> PPF -> SharedMLP(4,[32,64]) -> max over the neighbours
+fuser = ri_b200.modules.SharedMLP(4, [32, 64], dim=2).cuda().eval()
+folded = ri_b200.functional.fold_fuser(fuser)
+w1, b1, w2, b2 = folded
+
+
+def torch_branch():
+    with torch.no_grad():
+        return fuser(torch_block()).max(dim=2).values
+
+
+def torch_mlp_only(ppf):
+    with torch.no_grad():
+        return fuser(ppf).max(dim=2).values
+
+
+ppf = ri_b200.functional.ball_local_ppf(pts, nrm, R, U)
+e = t(lambda: torch.ops.ri.local_ppf_mlp_max(pts, nrm, pts, nrm, idx, w1, b1, w2, b2))
+f = t(lambda: ri_b200.functional.local_ppf_features(pts, nrm, folded, R, U))
+g = t(lambda: torch_mlp_only(ppf), 5)
+h = t(torch_branch, 5)
+flops = 2.0 * B * N * U * (4 * 32 + 32 * 64)
+print("local-feature branch [B,64,N]: fused kernel alone %8.1f us (%.1f useful TFLOP/s), with ball query %8.1f us | torch layers on a "
+      "ready PPF tensor %8.1f us, whole reference-style branch %8.1f us   -> %.1fx" % (e, flops / e / 1e6, f, g, h, h / f))
