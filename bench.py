@@ -65,7 +65,7 @@ for _r in (16, 64):
                                           "(BASELINE configs[4] sweep)" % _r)
 RING = 3            # independent input/output buffer sets cycled between timed steps (footprint > L2)
 LANES = 2           # steps in flight (tools/tune_lanes.py: cu_dg 140 / 149 / 149 us per step with 2 / 3 / 4 in flight, sph_dg 121 throughout)
-MIN_TIMED_MS = 250  # every timed region lasts at least this long
+MIN_TIMED_MS = float(os.environ.get("RI_BENCH_MIN_MS", "250"))  # every timed region lasts at least this long (env: profiling runs under ncu only)
 E2E_DEPTH = 4       # slots of the host-facing pipeline (tools/exp_e2e.py: 2 / 3 / 4 / 6 slots -> 0.578 / 0.579 / 0.547 / 0.552 ms per step)
 
 
