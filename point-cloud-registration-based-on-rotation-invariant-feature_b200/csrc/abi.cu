@@ -34,7 +34,6 @@ RiEnv& env_instance()
         e.ppf_maxl1 = env_int("RI_PPF_MAXL1", 0) == 1;
         e.match_pair = env_int("RI_MATCH_PAIR", -1);
         e.match_dbg = getenv("RI_MATCH_DBG") != nullptr;
-        e.fill_form = env_int("RI_FILL_FORM", -1);
         return e;
     }();
     return env;
@@ -58,9 +57,6 @@ extern "C" int ri_debug_set_knob(const char* name, int value)
     else if (!strcmp(name, "RI_FILL_LISTCAP")) e.fill_listcap = value;
     else if (!strcmp(name, "RI_FILL_RING")) e.fill_ring = value;
     else if (!strcmp(name, "RI_FILL_GROUP")) e.fill_group = value;
-    else if (!strcmp(name, "RI_FILL_FORM")) e.fill_form = value;
-    else if (!strcmp(name, "RI_FILL_CTAS")) e.fill_ctas = value;
-    else if (!strcmp(name, "RI_FILL_PAD_KB")) e.fill_pad_kb = value;
     else return RI_ERR_BAD_ARG;
     return RI_OK;
 }

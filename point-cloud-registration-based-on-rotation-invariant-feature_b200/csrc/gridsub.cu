@@ -19,14 +19,16 @@
 //
 // Pipeline (one stream, no host synchronisation, output count left in device memory):
 //   bounds   min / max corner: block reduction + atomicMin/Max on order-preserving integer images of the floats
-//   keys     64-bit cell index per point (+ iota), geometry recomputed per thread from the 6 bounds
-//   sort     cub::DeviceRadixSort::SortPairs (stable LSD radix sort; library plumbing, like the reference's
-//            unordered_map)
-//   heads    head flags -> exclusive scan (cub::DeviceScan) -> output slot of every cell; slot count = M
+//   keys     64-bit cell index per point (+ iota), geometry recomputed per thread from the 6 bounds; the largest key of
+//            the scan is kept in device memory (atomicMax)
+//   sort     this repo's stable LSD radix sort (csrc/radix.cuh) in the role of the reference's unordered_map: 8 passes are
+//            enqueued for the 64-bit keys, the passes above the largest key's top bit return at once (a 400k-point scan
+//            on a 4.5 cm grid has ~21 key bits: 3 passes run)
+//   heads    heads of the cell runs counted per block of 1024 sorted points, then every block sums the counts of the
+//            blocks before it and scans its own head flags: output slot of every cell; slot count = M
 //   reduce   one thread per (cell, channel) walks the cell's points in sorted (= original) order
 #include "ri_common.cuh"
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
+#include "radix.cuh"
 
 namespace {
 
@@ -63,6 +65,7 @@ __global__ void gs_init_kernel(unsigned* bounds, int* out_count)
     if (threadIdx.x < 3) bounds[threadIdx.x] = 0xffffffffu;
     else if (threadIdx.x < 6) bounds[threadIdx.x] = 0u;
     if (threadIdx.x == 6) *out_count = 0;
+    if (threadIdx.x == 7) *reinterpret_cast<unsigned long long*>(bounds + 8) = 0ull;          // the largest key
 }
 
 __global__ void __launch_bounds__(kGsThreads)
@@ -89,43 +92,119 @@ gs_bounds_kernel(const float* __restrict__ pts, int N, unsigned* __restrict__ bo
 
 __global__ void __launch_bounds__(kGsThreads)
 gs_keys_kernel(const float* __restrict__ pts, int N, float dl, const unsigned* __restrict__ bounds,
-               unsigned long long* __restrict__ keys, int* __restrict__ vals)
+               unsigned long long* __restrict__ keys, int* __restrict__ vals, unsigned long long* __restrict__ maxkey)
 {
     const int i = blockIdx.x * kGsThreads + threadIdx.x;
-    if (i >= N) return;
-    const GsGeom g = gs_geom(bounds, dl);
-    const unsigned long long ix = (unsigned long long)floorf(__fdiv_rn(__fsub_rn(pts[3 * (size_t)i + 0], g.ox), dl));
-    const unsigned long long iy = (unsigned long long)floorf(__fdiv_rn(__fsub_rn(pts[3 * (size_t)i + 1], g.oy), dl));
-    const unsigned long long iz = (unsigned long long)floorf(__fdiv_rn(__fsub_rn(pts[3 * (size_t)i + 2], g.oz), dl));
-    keys[i] = ix + g.nx * iy + g.nx * g.ny * iz;
-    vals[i] = i;
+    unsigned long long key = 0ull;
+    if (i < N) {
+        const GsGeom g = gs_geom(bounds, dl);
+        const unsigned long long ix = (unsigned long long)floorf(__fdiv_rn(__fsub_rn(pts[3 * (size_t)i + 0], g.ox), dl));
+        const unsigned long long iy = (unsigned long long)floorf(__fdiv_rn(__fsub_rn(pts[3 * (size_t)i + 1], g.oy), dl));
+        const unsigned long long iz = (unsigned long long)floorf(__fdiv_rn(__fsub_rn(pts[3 * (size_t)i + 2], g.oz), dl));
+        key = ix + g.nx * iy + g.nx * g.ny * iz;
+        keys[i] = key;
+        vals[i] = i;
+    }
+    // the largest key decides how many radix passes run (radix.cuh): one atomic per warp
+    unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    lo = hi == mhi ? lo : 0u;
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, lo);
+    if ((threadIdx.x & 31) == 0) atomicMax(maxkey, ((unsigned long long)mhi << 32) | mlo);
+}
+
+// Heads of the cell runs (a sorted point whose key differs from its predecessor's), kGsHeadItems points per thread.
+constexpr int kGsHeadItems = 4;
+constexpr int kGsHeadBlock = kGsThreads * kGsHeadItems;
+
+__device__ __forceinline__ const unsigned long long* gs_sorted_keys(const unsigned long long* ka, const unsigned long long* kb,
+                                                                   const unsigned long long* maxkey)
+{
+    return ri_radix::rs_result_in_b(maxkey, 64) ? kb : ka;
 }
 
 __global__ void __launch_bounds__(kGsThreads)
-gs_heads_kernel(const unsigned long long* __restrict__ keys, int N, int* __restrict__ flags)
+gs_count_kernel(const unsigned long long* __restrict__ ka, const unsigned long long* __restrict__ kb,
+                const unsigned long long* __restrict__ maxkey, int N, int* __restrict__ blockcnt)
 {
-    const int i = blockIdx.x * kGsThreads + threadIdx.x;
-    if (i >= N) return;
-    flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+    __shared__ int swarp[kGsThreads / 32];
+    const unsigned long long* keys = gs_sorted_keys(ka, kb, maxkey);
+    const int base = blockIdx.x * kGsHeadBlock + threadIdx.x * kGsHeadItems;
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < kGsHeadItems; ++e) {
+        const int i = base + e;
+        if (i < N && (i == 0 || keys[i] != keys[i - 1])) ++c;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) swarp[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < kGsThreads / 32; ++w) t += swarp[w];
+        blockcnt[blockIdx.x] = t;
+    }
 }
 
-// slot[i] = exclusive scan of the head flags; a head at i owns output cell slot[i]; the last thread publishes M
+// starts[slot] = first sorted position of output cell `slot`; starts[M] = N; *out_count = M
 __global__ void __launch_bounds__(kGsThreads)
-gs_starts_kernel(const int* __restrict__ flags, const int* __restrict__ slot, int N, int* __restrict__ starts,
-                 int* __restrict__ out_count)
+gs_starts_kernel(const unsigned long long* __restrict__ ka, const unsigned long long* __restrict__ kb,
+                 const unsigned long long* __restrict__ maxkey, int N, const int* __restrict__ blockcnt, int nblocks,
+                 int* __restrict__ starts, int* __restrict__ out_count)
 {
-    const int i = blockIdx.x * kGsThreads + threadIdx.x;
-    if (i >= N) return;
-    if (flags[i]) starts[slot[i]] = i;
-    if (i == N - 1) { const int M = slot[i] + flags[i]; *out_count = M; starts[M] = N; }
+    __shared__ int swarp[kGsThreads / 32];
+    __shared__ int sbefore;
+    const unsigned long long* keys = gs_sorted_keys(ka, kb, maxkey);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // heads in the blocks before this one
+    int part = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += kGsThreads) part += blockcnt[b];
+    part = __reduce_add_sync(0xffffffffu, part);
+    if (lane == 0) swarp[w] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int q = 0; q < kGsThreads / 32; ++q) t += swarp[q];
+        sbefore = t;
+    }
+    __syncthreads();
+    const int before = sbefore;
+    __syncthreads();
+    // this block's head flags, scanned in position order
+    const int base = blockIdx.x * kGsHeadBlock + threadIdx.x * kGsHeadItems;
+    bool head[kGsHeadItems];
+    int c = 0;
+#pragma unroll
+    for (int e = 0; e < kGsHeadItems; ++e) {
+        const int i = base + e;
+        head[e] = i < N && (i == 0 || keys[i] != keys[i - 1]);
+        c += head[e] ? 1 : 0;
+    }
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) swarp[w] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int q = 0; q < w; ++q) woff += swarp[q];
+    int slot = before + woff + incl - c;
+#pragma unroll
+    for (int e = 0; e < kGsHeadItems; ++e)
+        if (head[e]) starts[slot++] = base + e;
+    if (blockIdx.x == (unsigned)(nblocks - 1) && threadIdx.x == kGsThreads - 1) { *out_count = slot; starts[slot] = N; }
 }
 
 // one thread per (cell, channel): channel 0..2 = barycentre, 3..3+fdim-1 = features, then ldim label columns
 __global__ void __launch_bounds__(kGsThreads)
 gs_reduce_kernel(const float* __restrict__ pts, const float* __restrict__ feats, const int* __restrict__ labels,
-                 const int* __restrict__ order, const int* __restrict__ starts, const int* __restrict__ count_ptr,
+                 const int* __restrict__ order_a, const int* __restrict__ order_b, const unsigned long long* __restrict__ maxkey,
+                 const int* __restrict__ starts, const int* __restrict__ count_ptr,
                  int fdim, int ldim, float* __restrict__ out_pts, float* __restrict__ out_feats, int* __restrict__ out_labels)
 {
+    const int* order = ri_radix::rs_result_in_b(maxkey, 64) ? order_b : order_a;
     const int M = *count_ptr;
     const int chans = 3 + fdim + ldim;
     const long long total = (long long)M * chans;
@@ -183,29 +262,22 @@ gs_reduce_kernel(const float* __restrict__ pts, const float* __restrict__ feats,
 }
 
 struct GsLayout {
-    size_t bounds, keys_in, keys_out, vals_in, vals_out, flags, slot, starts, cub, cub_bytes, total;
+    size_t bounds, keys_in, keys_out, vals_in, vals_out, blockcnt, starts, hist, total;
 };
 
 static size_t gs_align(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static int gs_layout(int N, GsLayout& L)
 {
-    size_t sort_bytes = 0, scan_bytes = 0;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const unsigned long long*)nullptr,
-                                                    (unsigned long long*)nullptr, (const int*)nullptr, (int*)nullptr, N);
-    if (e != cudaSuccess) return (int)e;
-    e = cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, N);
-    if (e != cudaSuccess) return (int)e;
     size_t off = 0;
-    L.bounds = off; off += gs_align(8 * sizeof(unsigned));
+    L.bounds = off; off += gs_align(8 * sizeof(unsigned) + sizeof(unsigned long long));      // 6 bounds, pad, the largest key
     L.keys_in = off; off += gs_align((size_t)N * 8);
     L.keys_out = off; off += gs_align((size_t)N * 8);
     L.vals_in = off; off += gs_align((size_t)N * 4);
     L.vals_out = off; off += gs_align((size_t)N * 4);
-    L.flags = off; off += gs_align((size_t)N * 4);
-    L.slot = off; off += gs_align((size_t)N * 4);
+    L.blockcnt = off; off += gs_align(((size_t)N / kGsHeadBlock + 1) * 4);
     L.starts = off; off += gs_align(((size_t)N + 1) * 4);
-    L.cub = off; L.cub_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes; off += gs_align(L.cub_bytes);
+    L.hist = off; off += gs_align(ri_radix::hist_bytes(N));
     L.total = off;
     return RI_OK;
 }
@@ -241,28 +313,26 @@ extern "C" int ri_grid_subsample_f32(const float* points, const float* features,
     unsigned long long* keys_out = reinterpret_cast<unsigned long long*>(ws + L.keys_out);
     int* vals_in = reinterpret_cast<int*>(ws + L.vals_in);
     int* vals_out = reinterpret_cast<int*>(ws + L.vals_out);
-    int* flags = reinterpret_cast<int*>(ws + L.flags);
-    int* slot = reinterpret_cast<int*>(ws + L.slot);
+    int* blockcnt = reinterpret_cast<int*>(ws + L.blockcnt);
     int* starts = reinterpret_cast<int*>(ws + L.starts);
+    int* hist = reinterpret_cast<int*>(ws + L.hist);
+    unsigned long long* maxkey = reinterpret_cast<unsigned long long*>(bounds + 8);
     const int blocks = (N + kGsThreads - 1) / kGsThreads;
+    const int hblocks = (N + kGsHeadBlock - 1) / kGsHeadBlock;
     const int sms = ri_num_sms();
 
     gs_init_kernel<<<1, 32, 0, st>>>(bounds, out_count);
     gs_bounds_kernel<<<min(blocks, 8 * sms), kGsThreads, 0, st>>>(points, N, bounds);
-    gs_keys_kernel<<<blocks, kGsThreads, 0, st>>>(points, N, dl, bounds, keys_in, vals_in);
+    gs_keys_kernel<<<blocks, kGsThreads, 0, st>>>(points, N, dl, bounds, keys_in, vals_in, maxkey);
     RI_LAUNCH_CHECK();
-    size_t cub_bytes = L.cub_bytes;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(ws + L.cub, cub_bytes, keys_in, keys_out, vals_in, vals_out, N, 0, 64, st);
-    if (e != cudaSuccess) return (int)e;
-    gs_heads_kernel<<<blocks, kGsThreads, 0, st>>>(keys_out, N, flags);
-    cub_bytes = L.cub_bytes;
-    e = cub::DeviceScan::ExclusiveSum(ws + L.cub, cub_bytes, flags, slot, N, st);
-    if (e != cudaSuccess) return (int)e;
-    gs_starts_kernel<<<blocks, kGsThreads, 0, st>>>(flags, slot, N, starts, out_count);
+    const int rc_sort = ri_radix::sort_pairs<unsigned long long>(keys_in, keys_out, vals_in, vals_out, N, 64, maxkey, hist, st);
+    if (rc_sort != RI_OK) return rc_sort;
+    gs_count_kernel<<<hblocks, kGsThreads, 0, st>>>(keys_in, keys_out, maxkey, N, blockcnt);
+    gs_starts_kernel<<<hblocks, kGsThreads, 0, st>>>(keys_in, keys_out, maxkey, N, blockcnt, hblocks, starts, out_count);
     const long long work = (long long)N * (3 + fdim + ldim);
     const int rblocks = (int)min((long long)32 * sms, (work + kGsThreads - 1) / kGsThreads);
-    gs_reduce_kernel<<<rblocks, kGsThreads, 0, st>>>(points, features, labels, vals_out, starts, out_count, fdim, ldim,
-                                                      out_points, out_features, out_labels);
+    gs_reduce_kernel<<<rblocks, kGsThreads, 0, st>>>(points, features, labels, vals_in, vals_out, maxkey, starts, out_count, fdim,
+                                                      ldim, out_points, out_features, out_labels);
     RI_LAUNCH_CHECK();
     return RI_OK;
 }

@@ -32,7 +32,7 @@
 //   Fallback (N > 4096 points per cloud, r^3 not a multiple of 4, or misaligned pointers): memset + integer
 //   atomics for counts + float atomics for the means over a (point tile, channel group, cloud) grid.
 #include "ri_common.cuh"
-#include <cub/device/device_radix_sort.cuh>
+#include "radix.cuh"
 #include "prologue_math.cuh"
 #include <stdlib.h>
 
@@ -704,124 +704,18 @@ vox_fill_kernel(const float* __restrict__ means, const int* __restrict__ ws, int
     }
 }
 
-// ------------------------------------------------------------------------------------------------ K3, zero-stream form
-// ~97 % of the dense grid is zeros, and the ring form above still spends ~170 warp instructions per 8 KB tile on patching and
-// un-patching its shared-memory tiles (ncu: 4 warps per SM, each a serial chain of cp.async waits, bulk read-out waits and
-// proxy fences; DRAM at 48 %).  Here the zeros never pass through the SM's pipes at all: ONE constant zero tile per CTA is the
-// source of every bulk store (cp.async.bulk shared -> global: nothing to wait for before re-using it, any number of stores in
-// flight), and the tile's few occupied cells are written afterwards by ordinary 4-byte stores from the compact means table —
-// after the warp's issuing lane has seen the item's bulk group COMPLETE (cp.async.bulk.wait_group without .read: the zeros
-// are in L2), so the patches land on lines that are still dirty in L2 and merge there: DRAM sees every line once.
-// A work item is (cloud, tile, group of PG planes) from the same global counter; the zeros of item k + 1 are issued before
-// the patches of item k, and the first 64 cells' ids and values are loaded before the wait.
-constexpr int kZsWarps = 8;
-constexpr int kZsPlanes = 8;
-
-template <int PG>
-__global__ void __launch_bounds__(32 * kZsWarps)
-vox_fill_zs_kernel(const float* __restrict__ means, const int* __restrict__ ws, int b0, int B, int C, int N, int s,
-                   int tile_cells, int ntiles, int ucap, int* __restrict__ work_counter,
-                   float* __restrict__ out, int* __restrict__ cnt)
-{
-    extern __shared__ __align__(128) float szero[];       // [tile_cells] zeros, never written again
-    const int lane = threadIdx.x & 31;
-    const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-    const int warps = blockDim.x >> 5;
-    for (int i = threadIdx.x; i < tile_cells / 4; i += blockDim.x) reinterpret_cast<float4*>(szero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    ri_fence_proxy_async_smem();
-    __syncthreads();
-
-    const VoxWs L = vox_ws_layout(N, ntiles);
-    const int planes = C + 1;                              // plane C is the integer count grid
-    const int groups = (planes + PG - 1) / PG;
-    const int total_items = B * ntiles * groups;
-    const int nwarps = gridDim.x * warps;
-
-    auto draw = [&]() {                                    // next item number (valid in lane 0 until broadcast)
-        int v = 0;
-        if (lane == 0) v = nwarps + atomicAdd(work_counter, 1);
-        return v;
-    };
-    auto plane_ptr = [&](const FillItem& it, int p) -> float* {
-        return (p < C) ? out + ((size_t)it.b * C + p) * s : reinterpret_cast<float*>(cnt + (size_t)it.b * s);
-    };
-    auto issue_zeros = [&](const FillItem& it) {           // one bulk group per item
-        if (lane == 0) {
-            const int cell_lo = it.t * tile_cells;
-            const uint32_t bytes = (uint32_t)min(tile_cells, s - cell_lo) * 4u;
-            for (int p = it.p0; p < it.p1; ++p) ri_bulk_store(plane_ptr(it, p) + cell_lo, szero, bytes);
-            ri_bulk_commit();
-        }
-    };
-
-    FillItem cur, nxt;
-    fill_item_decode(cur, blockIdx.x * warps + wid, total_items, groups, PG, planes, ntiles, b0, ws, L);
-    int next_id = draw();
-    if (cur.bt >= 0) issue_zeros(cur);
-    next_id = __shfl_sync(0xffffffffu, next_id, 0);
-
-    while (cur.bt >= 0) {
-        fill_item_decode(nxt, next_id, total_items, groups, PG, planes, ntiles, b0, ws, L);
-        const int after = draw();                          // reply needed at the end of this item only
-        if (nxt.bt >= 0) issue_zeros(nxt);
-
-        const int* W = ws + (size_t)cur.b * L.stride;
-        const int n = cur.sB - cur.sA;                     // occupied cells of this tile
-        const int* cells = W + L.off_cell + cur.sA;
-        const int* starts = W + L.off_start + cur.sA;
-        const float* mrow = means + (size_t)cur.b * C * ucap + cur.sA;
-        // 64 cells at a time: ids and values of every plane in registers.  The first chunk is requested before the wait, every
-        // later one (crowded tiles of the spherical grid hold hundreds of cells) before the previous chunk is stored.
-        int cell[2], ncell[2];
-        float val[2][PG], nval[2][PG];
-        auto load_chunk = [&](int base, int (&cc)[2], float (&vv)[2][PG]) {
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = base + lane + 32 * h;
-                cc[h] = i < n ? __ldg(cells + i) : -1;
-#pragma unroll
-                for (int q = 0; q < PG; ++q) {
-                    const int p = cur.p0 + q;
-                    vv[h][q] = 0.f;
-                    if (i < n && p < cur.p1)
-                        vv[h][q] = p < C ? __ldg(mrow + (size_t)p * ucap + i) : __int_as_float(__ldg(starts + i + 1) - __ldg(starts + i));
-                }
-            }
-        };
-        load_chunk(0, cell, val);
-        if (lane == 0) {                                   // this item's zeros have landed (the next item's may be in flight)
-            if (nxt.bt >= 0) ri_bulk_wait<1>(); else ri_bulk_wait<0>();
-        }
-        __syncwarp();
-        for (int base = 0; base < n; base += 64) {
-            const bool more = base + 64 < n;
-            if (more) load_chunk(base + 64, ncell, nval);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (cell[h] >= 0) {
-#pragma unroll
-                    for (int q = 0; q < PG; ++q)
-                        if (cur.p0 + q < cur.p1) plane_ptr(cur, cur.p0 + q)[cell[h]] = val[h][q];
-                }
-            }
-            if (more) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    cell[h] = ncell[h];
-#pragma unroll
-                    for (int q = 0; q < PG; ++q) val[h][q] = nval[h][q];
-                }
-            }
-        }
-        cur = nxt;
-        next_id = __shfl_sync(0xffffffffu, after, 0);
-    }
-    if (lane == 0) {
-        ri_bulk_wait<0>();
-        // the last warp of the launch to run out of work resets the counters: the next launch on this workspace finds zeros
-        if (atomicAdd(work_counter + 1, 1) == nwarps - 1) { work_counter[1] = 0; __threadfence(); work_counter[0] = 0; }
-    }
-}
+// Measured and rejected in round 2 (all bit-identical to this kernel; tools/exp_zerostream.cu, profiles/r2_fill_experiments.md):
+//  * "zero-stream": every bulk store sourced from ONE constant zero tile, the occupied cells patched afterwards by ordinary
+//    4-byte stores once the issuing lane had seen the bulk group complete — 82-92 us against 59.  Zeros alone stream at
+//    6.0 TB/s from a constant tile (paced or not, like plain st.global.v4), but the patches need the FULL completion of the
+//    bulk group, and with more than ~16 bulk stores outstanding per SM the lines have left L2 when the patch arrives
+//    (5.25 TB/s at depth 1 x 8 warps, 2.5 TB/s at depth >= 4).  Patching in shared memory BEFORE the store keeps DRAM at one
+//    write per line: 5.9 TB/s for the bare pattern.
+//  * "register lists": the tile's cell offsets and the plane's values kept in registers (values loaded a plane ahead into
+//    alternating register sets) instead of cp.async-staged shared-memory lists — a third of the instructions per tile, yet
+//    60-61 us with 8 warps and 64-83 us with 4-6 (185 registers; crowded spherical tiles overflow 16 cells per lane).
+//  * small work items (2 planes) for the last 10-40 % of the (cloud, tile) pairs against the tail of the dynamic hand-out:
+//    58.1 us against 60.8 alone on the spherical grid, nothing on the cube grid, nothing with two batches in flight.
 
 // --------------------------------------------------------------------------------------- fallback path
 template <bool SPH>
@@ -950,23 +844,6 @@ int vox_fill_launch(int B, int C, int N, int s, int b0, int b1, const VoxPlan& p
     int* counter = vox_fill_counters(ws, plan, B, C, N) + 2 * (b0 % kMaxFillCalls);
     const RiEnv& env = ri_env();
     const int sms = ri_num_sms();
-    if (env.fill_form == 2) {
-        // zero-stream form: one constant zero tile per CTA, patches by ordinary stores once the zeros have landed
-        const int warps = (env.fill_warps >= 1 && env.fill_warps <= kFwMaxWarps) ? env.fill_warps : kZsWarps;
-        const int ctas = (env.fill_ctas >= 1 && env.fill_ctas <= 4) ? env.fill_ctas : 1;
-        const long long items = (long long)nb * plan.ntiles * ((C + 1 + kZsPlanes - 1) / kZsPlanes);
-        if (items > 0x7fffffffLL) return RI_ERR_UNSUPPORTED;
-        long long grid = (long long)ctas * sms;
-        const long long want = (items + warps - 1) / warps;
-        if (grid > want) grid = want;
-        size_t smem = (size_t)plan.tile_cells * sizeof(float);
-        if (env.fill_pad_kb >= 0 && env.fill_pad_kb <= 128) smem += (size_t)env.fill_pad_kb << 10;
-        RI_KERNEL_SETUP(vox_fill_zs_kernel<kZsPlanes>, true, ri_step_carveout_percent());
-        vox_fill_zs_kernel<kZsPlanes><<<(unsigned)grid, 32 * warps, smem, st>>>(means, ws, b0, nb, C, N, s, plan.tile_cells,
-                                                                              plan.ntiles, ucap, counter, out, cnt);
-        RI_LAUNCH_CHECK();
-        return RI_OK;
-    }
     const int ctas_per_sm = (env.fill_ctas >= 1 && env.fill_ctas <= 4) ? env.fill_ctas : kFillCtasPerSm;
     const int slots = (env.fill_ring >= 2 && env.fill_ring <= 4) ? env.fill_ring : kFwSlots;
     const int warps = (env.fill_warps >= 1 && env.fill_warps <= kFwMaxWarps) ? env.fill_warps : kFwWarps;
@@ -990,8 +867,8 @@ int vox_fill_launch(int B, int C, int N, int s, int b0, int b1, const VoxPlan& p
 // --------------------------------------------------------------------------------------- scan-sized clouds (N > 4096)
 // The same three phases — cell-sorted point list + occupied-cell table, compact cell means in ascending point order, dense
 // grid written once by vox_fill_kernel — for clouds that do not fit one CTA's shared-memory sort (ICL-NUIM-sized scans,
-// BASELINE configs[3]).  The (cloud, cell) keys of the whole batch go through ONE stable radix sort (cub::DeviceRadixSort,
-// library plumbing) of 32-bit keys  b * (s + 1) + cell  (cell = s for points outside the grid), the tables are rebuilt per
+// BASELINE configs[3]).  The (cloud, cell) keys of the whole batch go through ONE stable radix sort (csrc/radix.cuh:
+// ceil(bits / 8) passes) of 32-bit keys  b * (s + 1) + cell  (cell = s for points outside the grid), the tables are rebuilt per
 // cloud by a block-wide head-flag scan, and the means are summed per (cell, channel) thread in sorted = ascending point
 // order: deterministic and equal to the oracle bit for bit, where the atomic path's float atomicAdd order changes from
 // run to run (the reference has the same property).
@@ -1162,7 +1039,7 @@ vox_edge_large_kernel(const float* __restrict__ feat, const int* __restrict__ ws
     E[((size_t)C + c) * N + i] = f;
 }
 
-struct VoxLarge { size_t keys_in, keys_out, vals_in, vals_out, chunks, cub, cub_bytes, total; int bits, nchunks; };
+struct VoxLarge { size_t keys_in, keys_out, vals_in, vals_out, chunks, hist, total; int bits, nchunks; };
 
 // layout of the extra workspace of the scan-sized path, placed after the tables / means / counters of vox_ws_need
 static bool vox_large_layout(int B, int N, long long s, size_t base, VoxLarge& V)
@@ -1173,9 +1050,6 @@ static bool vox_large_layout(int B, int N, long long s, size_t base, VoxLarge& V
     while (bits < 32 && (1ll << bits) < nkeys) ++bits;
     V.bits = bits;
     const size_t n = (size_t)B * N;
-    size_t cb = 0;
-    if (cub::DeviceRadixSort::SortPairs(nullptr, cb, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr,
-                                        (int*)nullptr, (int)n, 0, bits) != cudaSuccess) return false;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t o = al(base);
     V.keys_in = o; o += al(n * 4);
@@ -1184,7 +1058,7 @@ static bool vox_large_layout(int B, int N, long long s, size_t base, VoxLarge& V
     V.vals_out = o; o += al(n * 4);
     V.nchunks = (N + kLgChunk - 1) / kLgChunk;
     V.chunks = o; o += al((size_t)B * V.nchunks * 2 * sizeof(int));
-    V.cub = o; V.cub_bytes = cb; o += al(cb);
+    V.hist = o; o += al(ri_radix::hist_bytes((long long)n));
     V.total = o;
     return true;
 }
@@ -1222,10 +1096,14 @@ int voxelize_impl(const float* feat, const void* coords, int B, int C, int N, in
             int* vals_out = reinterpret_cast<int*>(wb + V.vals_out);
             vox_keys_large_kernel<SPH><<<dim3((N + 255) / 256, B), 256, 0, st>>>(coords, N, r, s, ind, keys_in, vals_in);
             RI_LAUNCH_CHECK();
-            size_t cb = V.cub_bytes;
-            cudaError_t ec = cub::DeviceRadixSort::SortPairs(wb + V.cub, cb, keys_in, keys_out, vals_in, vals_out,
-                                                             (int)((size_t)B * N), 0, V.bits, st);
-            if (ec != cudaSuccess) return (int)ec;
+            // stable sort of the batch's (cloud, cell) keys: ceil(bits / 8) passes of this repo's radix sort (radix.cuh)
+            const int rcs = ri_radix::sort_pairs<unsigned>(keys_in, keys_out, vals_in, vals_out, (int)((size_t)B * N), V.bits,
+                                                           nullptr, reinterpret_cast<int*>(wb + V.hist), st);
+            if (rcs != RI_OK) return rcs;
+            if ((ri_radix::passes_for_bits(V.bits) & 1) == 0) {      // an even number of passes leaves the result in the first pair
+                unsigned* tk = keys_in; keys_in = keys_out; keys_out = tk;
+                int* tv = vals_in; vals_in = vals_out; vals_out = tv;
+            }
             int* chunks = reinterpret_cast<int*>(wb + V.chunks);
             vox_table_count_kernel<<<dim3(V.nchunks, B), kLgChunk, 0, st>>>(keys_out, N, s, V.nchunks, chunks);
             vox_table_scan_kernel<<<B, 32, 0, st>>>(N, plan.ntiles, V.nchunks, chunks, ws, vox_fill_counters(ws, plan, B, C, N));

@@ -132,3 +132,24 @@ def test_cuda_labels_in_large_cells(oracle):
     op, _, ol, _ = oracle.grid_subsample(pts, None, labels, 0.6)
     assert np.array_equal(sub_p.cpu().numpy(), op) and np.array_equal(sub_l.cpu().numpy(), ol)
     assert sub_p.shape[0] < 400 and took < 2.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extent,dl", [(0.1, 0.05), (0.5, 0.05), (3.0, 0.05), (40.0, 0.05), (100.0, 0.05), (300.0, 0.01),
+                                       (1000.0, 0.01), (3000.0, 0.01)])
+def test_cuda_sort_pass_counts(oracle, extent, dl):
+    """The radix sort of the cell keys runs ceil(bits / 8) passes, decided on the device from the largest key: from one pass
+    (64 cells) to eight (3 km at 1 cm: ~2^58 cells), odd and even counts (the result lands in either buffer), with
+    duplicate cells (stability: points of a cell are summed in input order) — all bit-equal to the C oracle."""
+    import torch
+    import ri_b200
+    rng = np.random.default_rng(int(extent * 7) % 1000)
+    N = 30011                                                     # not a multiple of the sort's 4096-pair tile
+    base = rng.uniform(-extent, extent, (N // 3, 3))
+    pts = np.concatenate([base, base + rng.uniform(0, dl * 0.3, base.shape), rng.uniform(-extent, extent, (N - 2 * (N // 3), 3))])
+    pts = pts[rng.permutation(N)].astype(np.float32)
+    feats = rng.standard_normal((N, 2)).astype(np.float32)
+    sub_p, sub_f = ri_b200.grid_sub_sampling(torch.from_numpy(pts).cuda(), features=torch.from_numpy(feats).cuda(), grid_size=dl)
+    op, of, _, keys = oracle.grid_subsample(pts, feats, None, dl)
+    assert np.array_equal(sub_p.cpu().numpy(), op) and np.array_equal(sub_f.cpu().numpy(), of)
+    assert np.all(keys[1:] > keys[:-1])                          # ascending cell order
