@@ -370,8 +370,15 @@ def measure_registration(ri_b200, H, rank, world):
     def step():
         xyz = both[:, :3].contiguous(); nrm = both[:, 3:].contiguous()
         _, _, ppf = torch.ops.ri.knn_ppf(xyz, nrm, k)                                       # [2P,4,k,N]
-        f = torch.tanh(torch.einsum("oc,bcn->bon", W1, ppf.reshape(2 * P, 4 * k, N)))
-        f = torch.einsum("oc,bcn->bon", W2, f).contiguous()                                 # [2P,512,N]
+        # the stand-in for the (out-of-scope, stock cuBLAS) dense layers runs as those do in the reference's default
+        # PyTorch configuration for convolutions: TF32 tensor cores (as fp32 SIMT GEMMs they were 1.8 of the job's 5.1 ms)
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            f = torch.tanh(torch.einsum("oc,bcn->bon", W1, ppf.reshape(2 * P, 4 * k, N)))
+            f = torch.einsum("oc,bcn->bon", W2, f).contiguous()                             # [2P,512,N]
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32
         m = mm(f[:P], f[P:])
         T, inl = ri_b200.registration.estimate_poses(p1, p2, m.idx1, m.idx2, m.count, func="ransac", seed=1)
         met = ri_b200.registration.registration_metrics(gt, T, p1)

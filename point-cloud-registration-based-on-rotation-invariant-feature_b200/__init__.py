@@ -21,6 +21,6 @@ from .backend import _backend  # noqa: F401
 from . import functional, modules  # noqa: F401
 from .frontend import FrontEnd, FrontEndLanes, FrontEndPipeline  # noqa: F401
 from . import shard, synth, matcher, subsampling, registration  # noqa: F401
-from .subsampling import grid_sub_sampling  # noqa: F401
+from .subsampling import grid_sub_sampling, grid_sub_sampling_many  # noqa: F401
 
 __version__ = '0.1.0'

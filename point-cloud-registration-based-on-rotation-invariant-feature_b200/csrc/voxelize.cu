@@ -296,12 +296,12 @@ vox_front_kernel(const float* __restrict__ points, int pstride, float* __restric
                  float* __restrict__ norm_coords, int* __restrict__ vox_coords, int* __restrict__ ind,
                  int* __restrict__ ws, float* __restrict__ means, float* __restrict__ edge)
 {
-    extern __shared__ unsigned long long skeys[];          // [P] sort keys
+    extern __shared__ __align__(16) unsigned long long skeys[];   // [P] sort keys
     int* scell = reinterpret_cast<int*>(skeys + P);        // [P] cell of each table slot
     int* spid = scell + P;                                 // [N] cell-sorted point ids
     int* sstart = spid + N;                                // [N + 1] first sorted slot of each table slot
     int* ssegof = sstart + N + 1;                          // [N] table slot of each point (-1 outside the grid)
-    float* sfeat = reinterpret_cast<float*>(ssegof + N + ((3 * N + 1) & 1));   // [kMeanChans][N + 4], 8-byte aligned
+    float* sfeat = reinterpret_cast<float*>(ssegof + N + ((4 - ((3 * N + 1) & 3)) & 3));   // [kMeanChans][N + 4], 16-byte aligned
     const int ld = N + 4;
     float* smean = sfeat + kMeanChans * ld;                // [kMeanChans][ucap]
     __shared__ float sred[kFrontThreads / 32];
@@ -320,10 +320,20 @@ vox_front_kernel(const float* __restrict__ points, int pstride, float* __restric
 
     // ---- this CTA's feature rows start flowing into shared memory now; they are first needed after the sort
     {
+        // 16 bytes per cp.async where the rows allow it: as 4-byte copies (16 LDGSTS per thread) the issue loop itself held half
+        // of the kernel's stall samples (ncu, round 2: the load/store unit's queue throttles the instructions behind it)
         const float* F = feat + ((size_t)b * C + c0) * N;
-        for (int e = tid; e < nch * N; e += kFrontThreads) {
-            const int j = e / N, i = e - j * N;
-            cp_async4(sfeat + j * ld + i, F + (size_t)j * N + i);
+        if ((N & 3) == 0 && (reinterpret_cast<uintptr_t>(F) & 15) == 0) {
+            const int n4 = N >> 2;
+            for (int e = tid; e < nch * n4; e += kFrontThreads) {
+                const int j = e / n4, i = (e - j * n4) << 2;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(ri_smem_u32(sfeat + j * ld + i)), "l"(F + (size_t)j * N + i) : "memory");
+            }
+        } else {
+            for (int e = tid; e < nch * N; e += kFrontThreads) {
+                const int j = e / N, i = e - j * N;
+                cp_async4(sfeat + j * ld + i, F + (size_t)j * N + i);
+            }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -1272,7 +1282,7 @@ extern "C" int ri_vox_front_f32(const float* points, int pstride, const float* m
     int* ws = reinterpret_cast<int*>(workspace);
     float* means = reinterpret_cast<float*>(ws + (size_t)B * plan.L.stride);
     const int ucap = (N + 3) / 4 * 4;
-    const size_t smem = (size_t)plan.P * (sizeof(unsigned long long) + sizeof(int)) + (size_t)(3 * N + 2) * sizeof(int) +
+    const size_t smem = (size_t)plan.P * (sizeof(unsigned long long) + sizeof(int)) + (size_t)(3 * N + 4) * sizeof(int) +
                         (size_t)kMeanChans * (N + 4 + ucap) * sizeof(float);
     auto kern = shape == 2 ? vox_front_kernel<true> : vox_front_kernel<false>;
     RI_KERNEL_SETUP(kern, true, ri_step_carveout_percent());

@@ -153,3 +153,30 @@ def test_cuda_sort_pass_counts(oracle, extent, dl):
     op, of, _, keys = oracle.grid_subsample(pts, feats, None, dl)
     assert np.array_equal(sub_p.cpu().numpy(), op) and np.array_equal(sub_f.cpu().numpy(), of)
     assert np.all(keys[1:] > keys[:-1])                          # ascending cell order
+
+
+@pytest.mark.gpu
+def test_cuda_many_scans_one_sync(oracle):
+    """grid_sub_sampling_many: several scans enqueued back to back, lengths read once — same results as one call per scan."""
+    import torch
+    import ri_b200
+    from ri_b200 import synth
+    rng = np.random.default_rng(3)
+    clouds = []
+    for q, n in enumerate((5000, 12345, 1, 40000)):
+        pts = np.ascontiguousarray(synth.make_scan(max(n, 16), seed=20 + q)[:3].T)[:n]
+        f = rng.standard_normal((n, 3)).astype(np.float32)
+        clouds.append((torch.from_numpy(pts).cuda(), torch.from_numpy(f).cuda() if q != 1 else None))
+    many = ri_b200.grid_sub_sampling_many(clouds, grid_size=0.07)
+    assert len(many) == len(clouds)
+    for (p, f), (mp, mf, ml) in zip(clouds, many):
+        one = ri_b200.grid_sub_sampling(p, features=f, grid_size=0.07)
+        op = one[0] if isinstance(one, tuple) else one
+        assert torch.equal(mp, op) and ml is None
+        if f is None:
+            assert mf is None
+        else:
+            assert torch.equal(mf, one[1])
+        ref_p, _, _, _ = oracle.grid_subsample(p.cpu().numpy(), None, None, 0.07)
+        assert np.array_equal(mp.cpu().numpy(), ref_p)
+    assert ri_b200.grid_sub_sampling_many([]) == []

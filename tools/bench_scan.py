@@ -34,6 +34,13 @@ def timed(fn):
 def subsample():
     return [ri_b200.grid_sub_sampling(r[:, :3].contiguous(), features=r[:, 3:].contiguous(), grid_size=a.cell) for r in raw]
 t_sub, subs = timed(subsample)
+
+
+def subsample_many():                      # the same scans through the batched call: one host synchronisation for all of them
+    return ri_b200.grid_sub_sampling_many([(r[:, :3].contiguous(), r[:, 3:].contiguous()) for r in raw], grid_size=a.cell)
+t_sub_many, subs_many = timed(subsample_many)
+assert all(torch.equal(p, q[0]) and torch.equal(f, q[1]) for (p, f), q in zip(subs, subs_many))
+t_sub_one, t_sub = t_sub, t_sub_many
 n = min(p.shape[0] for p, _ in subs)
 xyz = torch.stack([p[:n].t().contiguous() for p, _ in subs]).contiguous()                      # [B,3,n]
 nrm = torch.stack([torch.nn.functional.normalize(f[:n], dim=1).t().contiguous() for _, f in subs]).contiguous()
@@ -48,7 +55,7 @@ total = t_sub + t_knn + t_ppf + t_vox + t_dev
 print(json.dumps({"workload": "ICL-NUIM-shaped scans (BASELINE configs[3])", "scans": a.scans, "raw_points_per_scan": a.raw,
                   "cell_m": a.cell, "points_per_scan_after_subsampling": int(n), "k": a.k, "spherical_res": a.res,
                   "channels": a.channels,
-                  "ms": {"grid_subsample": t_sub, "knn_hash_grid": t_knn, "ppf_gather": t_ppf, "sph_voxelize": t_vox,
+                  "ms": {"grid_subsample": t_sub, "grid_subsample_one_call_per_scan": t_sub_one, "knn_hash_grid": t_knn, "ppf_gather": t_ppf, "sph_voxelize": t_vox,
                          "sph_devox": t_dev, "total": total},
                   "raw_points_per_s": a.scans * a.raw / (total * 1e-3),
                   "subsampled_points_per_s_knn_ppf_vox": a.scans * n / ((total - t_sub) * 1e-3),

@@ -1,5 +1,6 @@
 """Executed instructions and stall samples per SOURCE line of one profiled kernel.
-   python tools/ncu_lines.py <report.ncu-rep> <object.o> <kernel-name-substring> [source.cu]
+   [NCU_KERNEL=<regex>] python tools/ncu_lines.py <report.ncu-rep> <object.o> <kernel-name-substring> [source.cu]
+(NCU_KERNEL selects the kernel inside a report that holds several)
 Joins ncu's SASS-level source page (instruction order) with nvdisasm -g's line table of the same object."""
 import collections, csv, io, os, re, subprocess, sys, tempfile
 
@@ -21,7 +22,8 @@ for l in dis.splitlines():
         cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
     if re.match(r"\s+/\*[0-9a-f]{4}\*/", l):
         line_of.append(cur)
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+flt = ["--kernel-name", "regex:" + os.environ["NCU_KERNEL"], "--launch-count", "1"] if os.environ.get("NCU_KERNEL") else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + flt, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]; body = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
