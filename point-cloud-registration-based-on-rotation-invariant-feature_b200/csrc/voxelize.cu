@@ -406,16 +406,69 @@ vox_front_kernel(const float* __restrict__ points, int pstride, float* __restric
     __syncthreads();
 
     // ---- K1: bitonic sort of (cell, point), cell table (vox_prepare_kernel, tables kept in shared memory)
-    for (int size = 2; size <= P; size <<= 1) {
-        for (int j = size >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (P >> 1); t += kFrontThreads) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int l = i | j;
-                const unsigned long long a = skeys[i], c = skeys[l];
-                const bool up = (i & size) == 0;
-                if ((a > c) == up) { skeys[i] = c; skeys[l] = a; }
+    if (P == 2 * kFrontThreads && s < (1 << 21)) {
+        // 1024 keys, two per thread (elements 2 tid, 2 tid + 1), packed into 32 bits (cell << 10 | point; 0x3FFFFE = outside the
+        // grid, the same order as the 64-bit keys): the exchange distances 1 ... 32 stay inside a thread / a warp (min / max in
+        // registers, one shuffle per key), only the 10 steps with distance >= 64 go through shared memory (two 4 KB buffers
+        // alternate: one barrier per step).  The all-shared-memory network below took 55 barriers and 40 % of the kernel's
+        // instructions (ncu, round 2).
+        unsigned* const buf0 = reinterpret_cast<unsigned*>(skeys);
+        unsigned* const buf1 = buf0 + 2 * kFrontThreads;
+        auto pack = [&](unsigned long long k) -> unsigned {
+            if (k == ~0ull) return 0xFFFFFFFFu;                      // padding slot (N < 1024): behind everything
+            const unsigned c = (unsigned)(k >> 32);
+            return ((c == kNoCell ? 0x3FFFFEu : c) << 10) | ((unsigned)k & 1023u);
+        };
+        const unsigned long long in0 = skeys[2 * tid], in1 = skeys[2 * tid + 1];
+        unsigned k0 = pack(in0), k1 = pack(in1);
+        __syncthreads();                                             // every key is in registers: the buffers may be overwritten
+        const int lane_ = tid & 31;
+        int flip = 0;
+        for (int size = 2; size <= 2 * kFrontThreads; size <<= 1) {
+            const bool up = ((2 * tid) & size) == 0;
+            int j = size >> 1;
+            for (; j >= 64; j >>= 1) {
+                unsigned* const buf = flip ? buf1 : buf0;
+                buf[2 * tid] = k0; buf[2 * tid + 1] = k1;
+                __syncthreads();
+                const int pt = tid ^ (j >> 1);
+                const unsigned o0 = buf[2 * pt], o1 = buf[2 * pt + 1];
+                const bool take_min = (((2 * tid) & j) == 0) == up;
+                k0 = take_min ? min(k0, o0) : max(k0, o0);
+                k1 = take_min ? min(k1, o1) : max(k1, o1);
+                flip ^= 1;
             }
-            __syncthreads();
+            for (; j >= 2; j >>= 1) {
+                const unsigned o0 = __shfl_xor_sync(0xffffffffu, k0, j >> 1), o1 = __shfl_xor_sync(0xffffffffu, k1, j >> 1);
+                const bool take_min = ((lane_ & (j >> 1)) == 0) == up;
+                k0 = take_min ? min(k0, o0) : max(k0, o0);
+                k1 = take_min ? min(k1, o1) : max(k1, o1);
+            }
+            const unsigned lo = min(k0, k1), hi2 = max(k0, k1);
+            k0 = up ? lo : hi2;
+            k1 = up ? hi2 : lo;
+        }
+        __syncthreads();                                             // the last readers of the exchange buffers are done
+        auto unpack = [&](unsigned k) -> unsigned long long {
+            if (k == 0xFFFFFFFFu) return ~0ull;
+            const unsigned c = k >> 10;
+            return ((unsigned long long)(c == 0x3FFFFEu ? kNoCell : c) << 32) | (k & 1023u);
+        };
+        skeys[2 * tid] = unpack(k0);
+        skeys[2 * tid + 1] = unpack(k1);
+        __syncthreads();
+    } else {
+        for (int size = 2; size <= P; size <<= 1) {
+            for (int j = size >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (P >> 1); t += kFrontThreads) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int l = i | j;
+                    const unsigned long long a = skeys[i], c = skeys[l];
+                    const bool up = (i & size) == 0;
+                    if ((a > c) == up) { skeys[i] = c; skeys[l] = a; }
+                }
+                __syncthreads();
+            }
         }
     }
     const int E = (P + kFrontThreads - 1) / kFrontThreads;
@@ -528,12 +581,16 @@ vox_front_kernel(const float* __restrict__ points, int pstride, float* __restric
     // edge tensor is the input itself, which a caller on the far side of a PCIe link already holds
     const bool rel_only = (norm_mode & 0x200) != 0;
     float* Eo = edge + ((size_t)b * (rel_only ? 1 : 2) * C + c0) * N;
-    for (int e = tid; e < nch * N; e += kFrontThreads) {
-        const int j = e / N, i = e - j * N;
+    for (int i = tid; i < N; i += kFrontThreads) {                 // point outer, channel inner: no division, one table-slot load
         const int sg = ssegof[i];
-        const float f = sfeat[j * ld + i];
-        Eo[(size_t)j * N + i] = sg >= 0 ? __fsub_rn(f, smean[j * ucap + sg]) : 0.f;
-        if (!rel_only) Eo[((size_t)C + j) * N + i] = f;
+#pragma unroll
+        for (int j = 0; j < kMeanChans; ++j) {
+            if (j < nch) {
+                const float f = sfeat[j * ld + i];
+                Eo[(size_t)j * N + i] = sg >= 0 ? __fsub_rn(f, smean[j * ucap + sg]) : 0.f;
+                if (!rel_only) Eo[((size_t)C + j) * N + i] = f;
+            }
+        }
     }
 }
 

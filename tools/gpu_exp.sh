@@ -1,7 +1,8 @@
 #!/bin/bash
-OUT=gpurun_out/r2h; mkdir -p $OUT
-TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --nproc-per-node 2"
-timeout 300 $TR --master-port 29541 bench.py --gpus 2 --only > $OUT/n2_default.json 2>$OUT/n2_default.err
-NCCL_MAX_CTAS=1 timeout 300 $TR --master-port 29542 bench.py --gpus 2 --only > $OUT/n2_maxctas1.json 2>$OUT/n2_maxctas1.err
-NCCL_MAX_NCHANNELS=1 NCCL_MIN_NCHANNELS=1 timeout 300 $TR --master-port 29543 bench.py --gpus 2 --only > $OUT/n2_nch1.json 2>$OUT/n2_nch1.err
-for f in $OUT/n2_*.json; do echo $f; grep -o '"ms_per_step": [0-9.]*' $f | head -1; done
+OUT=gpurun_out/r2j; mkdir -p $OUT
+export RI_REQUIRE_REF=1
+timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_dropin_reference_python.py -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest.log
+for W in sph cube; do LANES=2 timeout 120 python tools/tune_lanes.py $W 2>&1 | tail -1 | tee -a $OUT/lanes.txt; done
+SHAPE=sph LANES=1 timeout 120 python tools/timeline_step.py 2>&1 | tee $OUT/timeline_sph_serial.txt
+SHAPE=cube LANES=1 timeout 120 python tools/timeline_step.py 2>&1 | tee $OUT/timeline_cube_serial.txt
+cat gpurun_out/parity_voxel_means_elementwise.json
