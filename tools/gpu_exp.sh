@@ -1,8 +1,4 @@
 #!/bin/bash
-OUT=gpurun_out/r2j; mkdir -p $OUT
-export RI_REQUIRE_REF=1
-timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_dropin_reference_python.py -m gpu -x -q > $OUT/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/pytest.log
-for W in sph cube; do LANES=2 timeout 120 python tools/tune_lanes.py $W 2>&1 | tail -1 | tee -a $OUT/lanes.txt; done
-SHAPE=sph LANES=1 timeout 120 python tools/timeline_step.py 2>&1 | tee $OUT/timeline_sph_serial.txt
-SHAPE=cube LANES=1 timeout 120 python tools/timeline_step.py 2>&1 | tee $OUT/timeline_cube_serial.txt
-cat gpurun_out/parity_voxel_means_elementwise.json
+OUT=gpurun_out/r2k; mkdir -p $OUT
+timeout 300 python tools/exp_devox_chans.py 2>&1 | tee $OUT/devox_chans.json
+for CH in 8 12 16; do RI_DEVOX_CHANS=$CH LANES=2 timeout 120 python tools/tune_lanes.py sph 2>&1 | tail -1 | tee -a $OUT/lanes.txt; done
