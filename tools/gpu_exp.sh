@@ -1,4 +1,5 @@
 #!/bin/bash
-OUT=gpurun_out/r2k; mkdir -p $OUT
-timeout 300 python tools/exp_devox_chans.py 2>&1 | tee $OUT/devox_chans.json
-for CH in 8 12 16; do RI_DEVOX_CHANS=$CH LANES=2 timeout 120 python tools/tune_lanes.py sph 2>&1 | tail -1 | tee -a $OUT/lanes.txt; done
+OUT=gpurun_out/r2m; mkdir -p $OUT
+export RI_BENCH_MIN_MS=0
+timeout 600 ncu --set full --clock-control none --import-source on -s 8 -c 2 -k regex:'vox_front' -o $OUT/front -f \
+  python bench.py --only --workload sph_dg --steps 2 --warmup 3 > $OUT/ncu.log 2>&1; echo "ncu rc=$?"

@@ -22,7 +22,7 @@ for l in dis.splitlines():
         cur = (os.path.basename(m.group(1)), int(m.group(2))); continue
     if re.match(r"\s+/\*[0-9a-f]{4}\*/", l):
         line_of.append(cur)
-flt = ["--kernel-name", "regex:" + os.environ["NCU_KERNEL"], "--launch-count", "1"] if os.environ.get("NCU_KERNEL") else []
+flt = ["--kernel-name", "regex:" + os.environ["NCU_KERNEL"], "--launch-skip", os.environ.get("NCU_SKIP", "0"), "--launch-count", "1"] if os.environ.get("NCU_KERNEL") else []
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + flt, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
