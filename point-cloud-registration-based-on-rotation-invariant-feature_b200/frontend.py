@@ -117,8 +117,6 @@ class FrontEnd:
             self._vox_coords = torch.empty((B, 3, N), dtype=i32, device=dev)
             self._ws_bytes = _L.ri_voxelize_workspace_bytes(B, C, N, r)
             self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device=dev)
-            # the HBM-bound voxel branch runs on the (high-priority) main stream of the step, the ALU-bound k-NN/PPF
-            # branch on a low-priority side stream: when both have CTAs pending, the grid writer is placed first
             # both branches at the same stream priority: with the k-NN / PPF branch on a lower-priority stream (round 1) the
             # block scheduler served every pending CTA of the other batch's voxel branch first and the side branch ran in the
             # gaps only — 107.8 against 102.6 us per step with two batches in flight (sph_dg), 126.0 against 118.1 (cu_dg)
