@@ -375,8 +375,9 @@ def measure_registration(ri_b200, H, rank, world):
         tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = True
         try:
-            f = torch.tanh(torch.einsum("oc,bcn->bon", W1, ppf.reshape(2 * P, 4 * k, N)))
-            f = torch.einsum("oc,bcn->bon", W2, f).contiguous()                             # [2P,512,N]
+            f = torch.tanh(torch.matmul(W1, ppf.reshape(2 * P, 4 * k, N)))                  # [2P,128,N]
+            f = torch.matmul(W2, f)                                                         # [2P,512,N], contiguous as produced
+            assert f.is_contiguous()
         finally:
             torch.backends.cuda.matmul.allow_tf32 = tf32
         m = mm(f[:P], f[P:])
