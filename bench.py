@@ -315,6 +315,22 @@ def measure_workload(key, args, ri_b200, H, rank, world, local, headline):
     for i in range(RING):
         vox_op(i)
     ms_fill, _ = H.timed(lambda n: [fill_only(i) for i in range(n)], args.steps)
+    # the same launches with the writers of consecutive batches in flight (one stream per buffer set): ramp and tail of one
+    # launch run under the next, which is how the step executes them
+    fill_streams = [torch.cuda.Stream(device=dev) for _ in range(RING)]
+
+    def fill_in_flight(n):
+        cur = torch.cuda.current_stream()
+        for s_ in fill_streams:
+            s_.wait_stream(cur)
+        for i in range(n):
+            fe = engines[i % RING]
+            rc = L.ri_voxelize_fill_f32(B, C, N, r, 0, B, fe.grid.data_ptr(), fe.cnt.data_ptr(), fe._ws.data_ptr(), fe._ws_bytes,
+                                        fill_streams[i % RING].cuda_stream)
+            assert rc == 0
+        for s_ in fill_streams:
+            cur.wait_stream(s_)
+    ms_fill_flight, _ = H.timed(fill_in_flight, args.steps)
     ms_devox, _ = H.timed(lambda n: [engines[i % RING]._devox(0, B, st) for i in range(n)], args.steps)
     ms_vox, _ = H.timed(lambda n: [vox_op(i) for i in range(n)], args.steps)
     ms_knn, _ = H.timed(lambda n: [engines[i % RING]._knn() for i in range(n)], args.steps)
@@ -328,6 +344,10 @@ def measure_workload(key, args, ri_b200, H, rank, world, local, headline):
         "achieved": fill_gbs, "peak": peak, "unit": "GB/s", "frac": fill_gbs / peak,
         "traffic": traffic_from_profile(key), "peak_source": peak_src,
         "algorithmic_bytes_per_launch": fill_bytes, "ms_per_launch": ms_fill,
+        "launches_in_flight": {"what": "the same launches on %d streams (one per buffer set): what a launch costs when its ramp and tail "
+                                       "run under its neighbours, as in the step" % RING,
+                               "ms_per_launch": ms_fill_flight, "achieved": fill_bytes / (ms_fill_flight * 1e-3) / 1e9,
+                               "frac": fill_bytes / (ms_fill_flight * 1e-3) / 1e9 / peak},
         "voxelize_op": {"kernels": ("vox_front (mean, prologue, cell sort, cell means, edge features) + vox_fill" if engines[0]._own_mean
                                     else "torch mean + vox_front (prologue, cell sort, cell means, edge features) + vox_fill"),
                         "algorithmic_bytes": alg["voxelize"], "ms": ms_vox, "achieved": vox_gbs, "frac": vox_gbs / peak},
