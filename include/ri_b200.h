@@ -232,7 +232,8 @@ int ri_grouping_backward_f32(const float* grad_y, const int* idx, int B, int C, 
  * reference's meter passes, deepgmr_mn40.py:121) when point_major != 0.
  *   diff[i,j] = |f1_i|^2 + |f2_j|^2 - 2 f1_i.f2_j           (3xTF32 split-precision tcgen05 contraction)
  *   corr12 [P,n1] = argmin_j diff, corr21 [P,n2] = argmin_i diff   (lowest index on ties, as np.argmin)
- *   dist12 [P,n1] = diff[i, corr12[i]] recomputed as an fp32 FMA chain
+ *   dist12 [P,n1] = diff[i, corr12[i]] recomputed as an fp32 FMA chain; NULL = indices only (what the reference's
+ *                   method returns): the re-evaluation pass over the descriptors is skipped
  *   idx1, idx2 [P,n1]: the mutual matches (corr21[corr12[i]] == i) in ascending i, count [P] of them, -1 beyond.
  * workspace >= ri_mutual_nn_workspace_bytes(P, C, n1, n2) bytes of device memory. */
 size_t ri_mutual_nn_workspace_bytes(int P, int C, int n1, int n2);

@@ -35,7 +35,7 @@ class MutualMatcher:
     """Pre-allocated, stream-ordered matcher for a fixed problem shape (what bench tools time): no per-call allocation,
     kernels enqueued straight through the C ABI."""
 
-    def __init__(self, P, C, n1, n2, point_major=False, device='cuda'):
+    def __init__(self, P, C, n1, n2, point_major=False, device='cuda', want_dist=True):
         from . import _lib
         self._L, self._check = _lib.lib, _lib.check
         self.P, self.C, self.n1, self.n2, self.point_major = int(P), int(C), int(n1), int(n2), bool(point_major)
@@ -45,7 +45,9 @@ class MutualMatcher:
         i32, dev = torch.int32, self.device
         self.corr12 = torch.empty((P, n1), dtype=i32, device=dev)
         self.corr21 = torch.empty((P, n2), dtype=i32, device=dev)
-        self.dist12 = torch.empty((P, n1), dtype=torch.float32, device=dev)
+        # want_dist=False: indices only, like the reference's find_correspondence_one_pair — skips the fp32 re-evaluation of
+        # the matched distances (the only pass of the finish that touches the descriptors)
+        self.dist12 = torch.empty((P, n1), dtype=torch.float32, device=dev) if want_dist else None
         self.idx1 = torch.empty((P, n1), dtype=i32, device=dev)
         self.idx2 = torch.empty((P, n1), dtype=i32, device=dev)
         self.count = torch.empty((P,), dtype=i32, device=dev)
@@ -56,7 +58,8 @@ class MutualMatcher:
         st = torch.cuda.current_stream().cuda_stream
         self._check(self._L.ri_mutual_nn_tf32x3(desc1.data_ptr(), desc2.data_ptr(), self.P, self.C, self.n1, self.n2,
                                                 1 if self.point_major else 0, self.corr12.data_ptr(),
-                                                self.corr21.data_ptr(), self.dist12.data_ptr(), self.idx1.data_ptr(),
+                                                self.corr21.data_ptr(),
+                                                self.dist12.data_ptr() if self.dist12 is not None else None, self.idx1.data_ptr(),
                                                 self.idx2.data_ptr(), self.count.data_ptr(), self._ws.data_ptr(),
                                                 self._nws, st), 'ri_mutual_nn')
         return self

@@ -203,3 +203,19 @@ def test_pair_and_single_cta_forms_agree(P, C, n1, n2, pm):
         L.ri_debug_set_knob(b"RI_MATCH_PAIR", -1)
     for k in res["0"]:
         assert torch.equal(res["0"][k], res["1"][k]), k
+
+
+@pytest.mark.parametrize("P,C,n1,n2,pm", [(3, 512, 1024, 1024, False), (2, 100, 300, 700, False), (2, 33, 1000, 130, True), (1, 16, 37, 53, False)])
+def test_indices_only_mode_equals_full_mode(P, C, n1, n2, pm):
+    """dist12 = NULL (the reference method returns (idx1, idx2) only): the distance re-evaluation is skipped, every other output is
+    the same as with it."""
+    import ri_b200
+    g = torch.Generator(device="cuda"); g.manual_seed(100 + C)
+    shp1, shp2 = ((P, n1, C), (P, n2, C)) if pm else ((P, C, n1), (P, C, n2))
+    d1 = torch.randn(shp1, device="cuda", generator=g); d2 = torch.randn(shp2, device="cuda", generator=g)
+    full = ri_b200.matcher.MutualMatcher(P, C, n1, n2, point_major=pm)
+    idx = ri_b200.matcher.MutualMatcher(P, C, n1, n2, point_major=pm, want_dist=False)
+    full(d1, d2); idx(d1, d2); torch.cuda.synchronize()
+    assert idx.dist12 is None
+    for name in ("corr12", "corr21", "idx1", "idx2", "count"):
+        assert torch.equal(getattr(full, name), getattr(idx, name)), name
