@@ -34,6 +34,7 @@ RiEnv& env_instance()
         e.ppf_maxl1 = env_int("RI_PPF_MAXL1", 0) == 1;
         e.match_pair = env_int("RI_MATCH_PAIR", -1);
         e.match_dbg = getenv("RI_MATCH_DBG") != nullptr;
+        e.match_tma = env_int("RI_MATCH_TMA", -1);
         return e;
     }();
     return env;
@@ -52,6 +53,7 @@ extern "C" int ri_debug_set_knob(const char* name, int value)
     else if (!strcmp(name, "RI_MATCH_PAIR")) e.match_pair = value;
     else if (!strcmp(name, "RI_DEVOX_DBG_SKIP")) e.devox_dbg_skip = value;
     else if (!strcmp(name, "RI_MATCH_DBG")) e.match_dbg = value;
+    else if (!strcmp(name, "RI_MATCH_TMA")) e.match_tma = value;
     else if (!strcmp(name, "RI_VOX_ATOMIC")) e.vox_atomic = value;
     else if (!strcmp(name, "RI_FILL_WARPS")) e.fill_warps = value;
     else if (!strcmp(name, "RI_FILL_LISTCAP")) e.fill_listcap = value;

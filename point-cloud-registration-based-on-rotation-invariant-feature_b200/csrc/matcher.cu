@@ -36,6 +36,8 @@
 //   * match_dist     per row of every pair: unpack c1, mutual flag, and the fp32 distance of the row's match from the
 //                    re-tiled descriptors;  match_compact  per pair: c2 and the ordered compaction (idx1, idx2, count).
 #include "ri_common.cuh"
+#include <cuda.h>
+#include <string.h>
 
 namespace {
 
@@ -171,6 +173,44 @@ match_prep_kernel(PrepSide s0, PrepSide s1, int C, int Cp, int point_major)
     }
 }
 
+// ------------------------------------------------------------------------------------------------ match_norm
+// The pre-pass of the no-image path (channel-major descriptors, indices only): squared norms (fp64 accumulate, rounded once, like
+// match_prep) and the reset of the argmin keys — one read of the descriptors at the HBM rate, nothing written but 8 bytes per
+// row.  CTA = 32 rows x 8 channel groups; a warp reads 128 contiguous bytes per channel.
+__global__ void __launch_bounds__(256)
+match_norm_kernel(PrepSide s0, PrepSide s1, int C)
+{
+    __shared__ double part[8][33];
+    const PrepSide S = blockIdx.z == 0 ? s0 : s1;
+    const int n = S.n, npad = S.npad;
+    const int cloud = blockIdx.y;
+    const int r0 = blockIdx.x * 32;
+    if (r0 >= npad) return;
+    const int lane = threadIdx.x & 31, cg = threadIdx.x >> 5;
+    const int row = r0 + lane;
+    const float* D = S.desc + (size_t)cloud * C * n + row;
+    double acc = 0.0;
+    if (row < n) {
+        int c = cg;
+        for (; c + 24 < C; c += 32) {                                 // four loads in flight
+            const float v0 = __ldg(D + (size_t)c * n), v1 = __ldg(D + (size_t)(c + 8) * n);
+            const float v2 = __ldg(D + (size_t)(c + 16) * n), v3 = __ldg(D + (size_t)(c + 24) * n);
+            acc = fma((double)v0, (double)v0, acc); acc = fma((double)v1, (double)v1, acc);
+            acc = fma((double)v2, (double)v2, acc); acc = fma((double)v3, (double)v3, acc);
+        }
+        for (; c < C; c += 8) { const float v = __ldg(D + (size_t)c * n); acc = fma((double)v, (double)v, acc); }
+    }
+    part[cg][lane] = acc;
+    __syncthreads();
+    if (cg == 0 && row < npad) {
+        double t = part[0][lane];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) t += part[q][lane];
+        S.nrm[(size_t)cloud * npad + row] = (float)t;
+        S.key[(size_t)cloud * npad + row] = ~0ull;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
@@ -196,6 +236,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// one box of a 3-D tensor map (columns, channels, pair) -> shared memory, completion on an mbarrier
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -529,6 +575,22 @@ static_assert(kStagesP % kConvGroupsP == 0, "each stage must belong to one conve
 constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
                              ((uint32_t)(kPairTileM >> 4) << 24);
 
+// The no-image path: operands straight from the channel-major descriptors [C, n] by tensor maps.  MN-major tf32 operands have
+// ONE legal shared-memory layout, the 128-byte swizzle with 32-byte atomicity (UMMA layout type 1 = SWIZZLE_128B_BASE32B, tensor-
+// map swizzle 128B_ATOM_32B: the 32-byte unit index, address bits 5-6, is XORed with the row index, bits 7-8): an atom is 4
+// channels x 32 rows of the operand = 4 rows of 128 bytes.  A box of 32 columns x 16 channels lands as 16 such rows = four atoms
+// in K; a 128-row operand is four boxes, 2 KB apart.  Descriptor: leading (MN) byte offset 2048 between the 32-row atoms, stride
+// (K) byte offset 512 between the 4-channel groups; one K = 8 step is two atoms deep, the second step of a stage starts 1024
+// bytes further.  Instruction descriptor: bits 15 / 16 = A / B are MN-major.  (With the 16-byte-atomicity 128B swizzle, type 2,
+// the kernel runs and every argmin is wrong — measured.)
+constexpr unsigned kMnLBO = 2048, kMnSBO = 512, kMnKStep = 1024;
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr)
+{
+    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)(kMnLBO >> 4) << 16) | ((uint64_t)(kMnSBO >> 4) << 32) |
+           (1ull << 46) | (1ull << 61);
+}
+constexpr uint32_t kIdesc2Mn = kIdesc2 | (1u << 15) | (1u << 16);
+
 __device__ __forceinline__ uint32_t cluster_ctarank()
 {
     uint32_t r;
@@ -577,12 +639,14 @@ __device__ __forceinline__ void tc_mma2_tf32(uint32_t tmem_d, uint64_t adesc, ui
         "}\n" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 
+template <bool TMA>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPThreadsP, 1)
 match_gemm_pair_kernel(const float* __restrict__ img1, const float* __restrict__ img2,
                   const float* __restrict__ nrm1, const float* __restrict__ nrm2,
                   int n1, int n2, int n1p, int n2p, int Cp, int tiles_m, int tiles_n, int total_tiles,
                   unsigned long long* __restrict__ rowkey, unsigned long long* __restrict__ colkey,
-                  unsigned long long* __restrict__ dbg)
+                  unsigned long long* __restrict__ dbg,
+                  const __grid_constant__ CUtensorMap tmap1, const __grid_constant__ CUtensorMap tmap2)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -653,8 +717,16 @@ match_gemm_pair_kernel(const float* __restrict__ img1, const float* __restrict__
                     const uint32_t bar = ri_smem_u32(&S->raw[s]);
                     mbar_expect_tx(bar, kABytes + kB2Bytes);
                     const uint32_t dst = ring + s * kStage2Bytes;
-                    bulk_g2s(dst + kAHi, A + (size_t)kc * planeA + (size_t)m0 * kRowBytes, kABytes, bar);
-                    bulk_g2s(dst + kBHi, B + (size_t)kc * planeB + (size_t)(c0 + (int)rank * kHalfN) * kRowBytes, kB2Bytes, bar);
+                    if constexpr (TMA) {                          // four boxes of 32 rows x 16 channels per operand
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            tma_load_3d(dst + kAHi + q * 2048, &tmap1, m0 + 32 * q, kc * kChunkK, pair, bar);
+                            tma_load_3d(dst + kBHi + q * 2048, &tmap2, c0 + (int)rank * kHalfN + 32 * q, kc * kChunkK, pair, bar);
+                        }
+                    } else {
+                        bulk_g2s(dst + kAHi, A + (size_t)kc * planeA + (size_t)m0 * kRowBytes, kABytes, bar);
+                        bulk_g2s(dst + kBHi, B + (size_t)kc * planeB + (size_t)(c0 + (int)rank * kHalfN) * kRowBytes, kB2Bytes, bar);
+                    }
                 }
             }
         }
@@ -676,12 +748,21 @@ match_gemm_pair_kernel(const float* __restrict__ img1, const float* __restrict__
                     const uint32_t base = ring + s * kStage2Bytes;
 #pragma unroll
                     for (int ks = 0; ks < kChunkK / 8; ++ks) {
-                        const uint32_t koff = ks * 2 * kLBO;     // one K-step = two 16-byte k-cores
-                        const uint64_t a_hi = smem_desc(base + kAHi + koff), a_lo = smem_desc(base + kALo + koff);
-                        const uint64_t b_hi = smem_desc(base + kBHi + koff), b_lo = smem_desc(base + kBLo + koff);
-                        tc_mma2_tf32(acc, a_lo, b_hi, kIdesc2, (kc | ks) != 0);    // small terms first
-                        tc_mma2_tf32(acc, a_hi, b_lo, kIdesc2, 1);
-                        tc_mma2_tf32(acc, a_hi, b_hi, kIdesc2, 1);
+                        if constexpr (TMA) {
+                            const uint32_t koff = ks * kMnKStep; // one K-step = the next 8 channels = two atoms deeper
+                            const uint64_t a_hi = smem_desc_mn(base + kAHi + koff), a_lo = smem_desc_mn(base + kALo + koff);
+                            const uint64_t b_hi = smem_desc_mn(base + kBHi + koff), b_lo = smem_desc_mn(base + kBLo + koff);
+                            tc_mma2_tf32(acc, a_lo, b_hi, kIdesc2Mn, (kc | ks) != 0);
+                            tc_mma2_tf32(acc, a_hi, b_lo, kIdesc2Mn, 1);
+                            tc_mma2_tf32(acc, a_hi, b_hi, kIdesc2Mn, 1);
+                        } else {
+                            const uint32_t koff = ks * 2 * kLBO;     // one K-step = two 16-byte k-cores
+                            const uint64_t a_hi = smem_desc(base + kAHi + koff), a_lo = smem_desc(base + kALo + koff);
+                            const uint64_t b_hi = smem_desc(base + kBHi + koff), b_lo = smem_desc(base + kBLo + koff);
+                            tc_mma2_tf32(acc, a_lo, b_hi, kIdesc2, (kc | ks) != 0);    // small terms first
+                            tc_mma2_tf32(acc, a_hi, b_lo, kIdesc2, 1);
+                            tc_mma2_tf32(acc, a_hi, b_hi, kIdesc2, 1);
+                        }
                     }
                     tc_commit2(ri_smem_u32(&S->empty[s]));       // stage reusable in BOTH CTAs once these MMAs have read it
                 }
@@ -696,7 +777,10 @@ match_gemm_pair_kernel(const float* __restrict__ img1, const float* __restrict__
         //      on it (31 % busy); kConvGroupsP groups convert that many stages at the same time.
         const int ct = t - kConvWarp0 * 32;
         const int grp = ct >> 7, tg = ct & 127;
-        const uint32_t slot_a = (uint32_t)(tg >> 3) * kSBO + (uint32_t)(tg & 7) * 16;      // row tg inside a plane
+        // K-major image: row tg of a plane, its four k-cores 128 bytes apart.  Tensor-map path: the split is element-wise, so
+        // any one-to-one walk over the plane's 512 16-byte slots does: slot tg + 128 q.
+        const uint32_t slot_a = TMA ? (uint32_t)tg * 16 : (uint32_t)(tg >> 3) * kSBO + (uint32_t)(tg & 7) * 16;
+        constexpr uint32_t kSlotStep = TMA ? 128 * 16 : kLBO;
         const uint32_t full_leader = mapa_shared(ri_smem_u32(&S->full[0]), 0);
         const int total = my_tiles * nk;
         for (int g = grp; g < total; g += kConvGroupsP) {
@@ -707,18 +791,18 @@ match_gemm_pair_kernel(const float* __restrict__ img1, const float* __restrict__
             float4 v[8];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                v[2 * q + 0] = *reinterpret_cast<const float4*>(st + kAHi + slot_a + q * kLBO);
-                v[2 * q + 1] = *reinterpret_cast<const float4*>(st + kBHi + slot_a + q * kLBO);
+                v[2 * q + 0] = *reinterpret_cast<const float4*>(st + kAHi + slot_a + q * kSlotStep);
+                v[2 * q + 1] = *reinterpret_cast<const float4*>(st + kBHi + slot_a + q * kSlotStep);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float4 h, l;
                 split4(v[2 * q + 0], h, l);
-                if (kWriteHi) *reinterpret_cast<float4*>(st + kAHi + slot_a + q * kLBO) = h;
-                *reinterpret_cast<float4*>(st + kALo + slot_a + q * kLBO) = l;
+                if (kWriteHi) *reinterpret_cast<float4*>(st + kAHi + slot_a + q * kSlotStep) = h;
+                *reinterpret_cast<float4*>(st + kALo + slot_a + q * kSlotStep) = l;
                 split4(v[2 * q + 1], h, l);
-                if (kWriteHi) *reinterpret_cast<float4*>(st + kBHi + slot_a + q * kLBO) = h;
-                *reinterpret_cast<float4*>(st + kBLo + slot_a + q * kLBO) = l;
+                if (kWriteHi) *reinterpret_cast<float4*>(st + kBHi + slot_a + q * kSlotStep) = h;
+                *reinterpret_cast<float4*>(st + kBLo + slot_a + q * kSlotStep) = l;
             }
             ri_fence_proxy_async_smem();                     // generic-proxy stores -> visible to the tensor core's reads
             __syncwarp();
@@ -905,6 +989,39 @@ match_compact_kernel(int n1, int n2, int n1p, int n2p, const unsigned long long*
 
 }  // namespace
 
+// tensor map of channel-major descriptors [P][C][n] (n innermost): box = 32 columns x 16 channels of one pair, 128-byte swizzle
+// with 32-byte atomicity (the one layout MN-major tf32 operands accept), out-of-range columns / channels read as zeros (so neither n
+// nor C needs padding)
+// (the driver entry point is looked up through the runtime, not linked: the library must load on machines without libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn match_encode_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+static bool match_make_tmap(CUtensorMap* map, const float* desc, int P, int C, int n)
+{
+    const EncodeTiledFn cuTensorMapEncodeTiled = match_encode_fn();
+    if (cuTensorMapEncodeTiled == nullptr) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)n, (cuuint64_t)C, (cuuint64_t)P};
+    const cuuint64_t strides[2] = {(cuuint64_t)n * sizeof(float), (cuuint64_t)C * n * sizeof(float)};
+    const cuuint32_t box[3] = {32u, (cuuint32_t)kChunkK, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(desc), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 extern "C" size_t ri_mutual_nn_workspace_bytes(int P, int C, int n1, int n2)
 {
     if (P <= 0 || C <= 0 || n1 <= 0 || n2 <= 0) return 16;
@@ -935,6 +1052,37 @@ extern "C" int ri_mutual_nn_tf32x3(const float* desc1, const float* desc2, int P
     unsigned long long* colkey = reinterpret_cast<unsigned long long*>(ws + L.colkey);
 
     const PrepSide side1 = {desc1, img1, nrm1, rowkey, n1, L.n1p}, side2 = {desc2, img2, nrm2, colkey, n2, L.n2p};
+    const RiEnv& env0 = ri_env();
+    // No-image path: indices only (nothing re-reads the descriptors afterwards), channel-major input, CTA-pair GEMM: the operands
+    // come straight from the descriptors through tensor maps (MN-major UMMA operands), the pre-pass shrinks to the norms.
+    const bool pair_ok = env0.match_pair >= 0 ? env0.match_pair == 1 : (n1 > kTileM && ri_num_sms() >= 2);
+    CUtensorMap tm1, tm2;
+    bool tma_path = dist12 == nullptr && !point_major && pair_ok && env0.match_tma != 0 && !env0.match_dbg &&
+                    (n1 % 4 == 0) && (n2 % 4 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(desc1) | reinterpret_cast<uintptr_t>(desc2)) & 15) == 0;
+    if (tma_path) tma_path = match_make_tmap(&tm1, desc1, P, C, n1) && match_make_tmap(&tm2, desc2, P, C, n2);
+    if (tma_path) {
+        const int norm_x = (L.n1p > L.n2p ? L.n1p : L.n2p) / 32;
+        match_norm_kernel<<<dim3(norm_x, P, 2), 256, 0, st>>>(side1, side2, C);
+        RI_LAUNCH_CHECK();
+        const size_t smem2 = (size_t)kStagesP * kStage2Bytes + sizeof(GemmSmem) + 1024;
+        RI_KERNEL_SETUP(match_gemm_pair_kernel<true>, true, -1);
+        const int tiles_n = L.n2p / kTileN;
+        const int ptiles_m = (n1 + kPairTileM - 1) / kPairTileM;
+        const long long ptotal = (long long)P * ptiles_m * tiles_n;
+        if (ptotal > 0x7fffffffLL) return RI_ERR_UNSUPPORTED;
+        int clusters = ri_num_sms() / 2;
+        if (ptotal < clusters) clusters = (int)ptotal;
+        match_gemm_pair_kernel<true><<<2 * clusters, kPThreadsP, smem2, st>>>(nullptr, nullptr, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp,
+                                                                              ptiles_m, tiles_n, (int)ptotal, rowkey, colkey, nullptr,
+                                                                              tm1, tm2);
+        RI_LAUNCH_CHECK();
+        int* mutual_t = reinterpret_cast<int*>(ws + L.mutual);
+        match_unpack_kernel<<<dim3((n1 + 255) / 256, P), 256, 0, st>>>(n1, n2, L.n1p, L.n2p, rowkey, colkey, corr12, mutual_t);
+        match_compact_kernel<<<P, kFinThreads, 0, st>>>(n1, n2, L.n1p, L.n2p, colkey, corr12, mutual_t, corr21, idx1, idx2, count);
+        RI_LAUNCH_CHECK();
+        return RI_OK;
+    }
     const int prep_x = (L.n1p > L.n2p ? L.n1p : L.n2p) / kPrepRows;
     match_prep_kernel<<<dim3(prep_x, P, 2), kPrepThreads, 0, st>>>(side1, side2, C, L.Cp, point_major);
     RI_LAUNCH_CHECK();
@@ -952,13 +1100,16 @@ extern "C" int ri_mutual_nn_tf32x3(const float* desc1, const float* desc2, int P
         if (pair_form) {
             // CTA pairs over 256 x 256 tiles (cta_group::2)
             const size_t smem2 = (size_t)kStagesP * kStage2Bytes + sizeof(GemmSmem) + 1024;
-            RI_KERNEL_SETUP(match_gemm_pair_kernel, true, -1);
+            RI_KERNEL_SETUP(match_gemm_pair_kernel<false>, true, -1);
+            CUtensorMap none;
+            memset(&none, 0, sizeof(none));
             const int ptiles_m = (n1 + kPairTileM - 1) / kPairTileM;
             const long long ptotal = (long long)P * ptiles_m * tiles_n;
             int clusters = ri_num_sms() / 2;
             if (ptotal < clusters) clusters = (int)ptotal;
-            match_gemm_pair_kernel<<<2 * clusters, kPThreadsP, smem2, st>>>(img1, img2, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp,
-                                                                          ptiles_m, tiles_n, (int)ptotal, rowkey, colkey, dbg);
+            match_gemm_pair_kernel<false><<<2 * clusters, kPThreadsP, smem2, st>>>(img1, img2, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp,
+                                                                                 ptiles_m, tiles_n, (int)ptotal, rowkey, colkey, dbg,
+                                                                                 none, none);
         } else {
             RI_KERNEL_SETUP(match_gemm_kernel, true, -1);
             match_gemm_kernel<<<grid, kPThreads, smem, st>>>(img1, img2, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp, tiles_m, tiles_n,

@@ -44,6 +44,7 @@ struct RiEnv {
     int ppf_maxl1;                          // RI_PPF_MAXL1          packed PPF kernel keeps the default (max-L1) split
     int match_pair;                         // RI_MATCH_PAIR         -1 unset, 0 single-CTA form, 1 CTA-pair form
     int match_dbg;                          // RI_MATCH_DBG          GEMM only, %globaltimer stamps in the workspace
+    int match_tma;                          // RI_MATCH_TMA          0: never take the tensor-map (no-image) path of the indices-only matcher
 };
 // One instance per process, defined in abi.cu; initialised on first use (thread-safe), read-only on every launch path.
 // ri_debug_set_knob() (tests, tools) overwrites a field — not while launches are in flight on other threads.

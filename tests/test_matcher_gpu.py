@@ -205,10 +205,13 @@ def test_pair_and_single_cta_forms_agree(P, C, n1, n2, pm):
         assert torch.equal(res["0"][k], res["1"][k]), k
 
 
-@pytest.mark.parametrize("P,C,n1,n2,pm", [(3, 512, 1024, 1024, False), (2, 100, 300, 700, False), (2, 33, 1000, 130, True), (1, 16, 37, 53, False)])
+@pytest.mark.parametrize("P,C,n1,n2,pm", [(3, 512, 1024, 1024, False), (2, 100, 300, 700, False), (2, 33, 1000, 130, True), (1, 16, 37, 53, False),
+                                          (2, 33, 1000, 132, False), (3, 70, 301, 515, False), (5, 128, 1024, 512, False), (2, 256, 260, 1028, False)])
 def test_indices_only_mode_equals_full_mode(P, C, n1, n2, pm):
     """dist12 = NULL (the reference method returns (idx1, idx2) only): the distance re-evaluation is skipped, every other output is
-    the same as with it."""
+    the same as with it.  For channel-major descriptors with n1 > 128 and n % 4 == 0 the indices-only call takes the no-image path
+    (operands through tensor maps as MN-major UMMA operands, norms by their own kernel): it must return the same bits as the
+    pre-pass path, also where columns / channels run past the tensor (C not a multiple of 16, n not a multiple of 32 or 256)."""
     import ri_b200
     g = torch.Generator(device="cuda"); g.manual_seed(100 + C)
     shp1, shp2 = ((P, n1, C), (P, n2, C)) if pm else ((P, C, n1), (P, C, n2))
@@ -219,3 +222,24 @@ def test_indices_only_mode_equals_full_mode(P, C, n1, n2, pm):
     assert idx.dist12 is None
     for name in ("corr12", "corr21", "idx1", "idx2", "count"):
         assert torch.equal(getattr(full, name), getattr(idx, name)), name
+
+
+def test_indices_only_stress_two_streams():
+    """The tensor-map form of the persistent CTA-pair GEMM under the same stress as the pre-pass form: 300 calls alternating
+    between two streams, every call reproduces the first call's bits (and none hangs)."""
+    import ri_b200
+    for (P, C, n1, n2) in ((32, 512, 1024, 1024), (5, 100, 300, 700)):
+        g = torch.Generator(device="cuda"); g.manual_seed(P)
+        d1 = torch.randn((P, C, n1), device="cuda", generator=g); d2 = torch.randn((P, C, n2), device="cuda", generator=g)
+        mms = [ri_b200.matcher.MutualMatcher(P, C, n1, n2, want_dist=False) for _ in range(2)]
+        streams = [torch.cuda.Stream() for _ in range(2)]
+        mms[0](d1, d2); torch.cuda.synchronize()
+        want = (mms[0].corr12.clone(), mms[0].corr21.clone(), mms[0].idx1.clone(), mms[0].count.clone())
+        for it in range(300):
+            q = it & 1
+            with torch.cuda.stream(streams[q]):
+                mms[q](d1, d2)
+        torch.cuda.synchronize()
+        for mm in mms:
+            assert torch.equal(mm.corr12, want[0]) and torch.equal(mm.corr21, want[1])
+            assert torch.equal(mm.idx1, want[2]) and torch.equal(mm.count, want[3])
