@@ -192,11 +192,12 @@ match_norm_kernel(PrepSide s0, PrepSide s1, int C)
     double acc = 0.0;
     if (row < n) {
         int c = cg;
-        for (; c + 24 < C; c += 32) {                                 // four loads in flight
-            const float v0 = __ldg(D + (size_t)c * n), v1 = __ldg(D + (size_t)(c + 8) * n);
-            const float v2 = __ldg(D + (size_t)(c + 16) * n), v3 = __ldg(D + (size_t)(c + 24) * n);
-            acc = fma((double)v0, (double)v0, acc); acc = fma((double)v1, (double)v1, acc);
-            acc = fma((double)v2, (double)v2, acc); acc = fma((double)v3, (double)v3, acc);
+        for (; c + 56 < C; c += 64) {                                 // eight loads in flight
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = __ldg(D + (size_t)(c + 8 * q) * n);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc = fma((double)v[q], (double)v[q], acc);
         }
         for (; c < C; c += 8) { const float v = __ldg(D + (size_t)c * n); acc = fma((double)v, (double)v, acc); }
     }
@@ -242,6 +243,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -646,7 +652,7 @@ match_gemm_pair_kernel(const float* __restrict__ img1, const float* __restrict__
                   int n1, int n2, int n1p, int n2p, int Cp, int tiles_m, int tiles_n, int total_tiles,
                   unsigned long long* __restrict__ rowkey, unsigned long long* __restrict__ colkey,
                   unsigned long long* __restrict__ dbg,
-                  const __grid_constant__ CUtensorMap tmap1, const __grid_constant__ CUtensorMap tmap2)
+                  const __grid_constant__ CUtensorMap tmap1, const __grid_constant__ CUtensorMap tmap2, int tma4)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -718,6 +724,10 @@ match_gemm_pair_kernel(const float* __restrict__ img1, const float* __restrict__
                     mbar_expect_tx(bar, kABytes + kB2Bytes);
                     const uint32_t dst = ring + s * kStage2Bytes;
                     if constexpr (TMA) {                          // four boxes of 32 rows x 16 channels per operand
+                        if (tma4) {                               // ... as one 4-D box each where the tensor allows it
+                            tma_load_4d(dst + kAHi, &tmap1, 0, kc * kChunkK, m0 >> 5, pair, bar);
+                            tma_load_4d(dst + kBHi, &tmap2, 0, kc * kChunkK, (c0 + (int)rank * kHalfN) >> 5, pair, bar);
+                        } else
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             tma_load_3d(dst + kAHi + q * 2048, &tmap1, m0 + 32 * q, kc * kChunkK, pair, bar);
@@ -1009,6 +1019,21 @@ static EncodeTiledFn match_encode_fn()
     }();
     return fn;
 }
+// 4-D form of the same tensor (n % 32 == 0): (32 columns | C channels | n / 32 column blocks | P pairs) with the column-block
+// stride (128 B) BELOW the channel stride (4 n B), so that one box of 32 x 16 x 4 x 1 lands exactly as the four 3-D boxes of an
+// operand do, in one instruction instead of four.
+static bool match_make_tmap4(CUtensorMap* map, const float* desc, int P, int C, int n)
+{
+    const EncodeTiledFn cuTensorMapEncodeTiled = match_encode_fn();
+    if (cuTensorMapEncodeTiled == nullptr || (n & 31) != 0) return false;
+    const cuuint64_t dims[4] = {32u, (cuuint64_t)C, (cuuint64_t)(n / 32), (cuuint64_t)P};
+    const cuuint64_t strides[3] = {(cuuint64_t)n * sizeof(float), 128u, (cuuint64_t)C * n * sizeof(float)};
+    const cuuint32_t box[4] = {32u, (cuuint32_t)kChunkK, 4u, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    return cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(desc), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 static bool match_make_tmap(CUtensorMap* map, const float* desc, int P, int C, int n)
 {
     const EncodeTiledFn cuTensorMapEncodeTiled = match_encode_fn();
@@ -1060,7 +1085,11 @@ extern "C" int ri_mutual_nn_tf32x3(const float* desc1, const float* desc2, int P
     bool tma_path = dist12 == nullptr && !point_major && pair_ok && env0.match_tma != 0 && !env0.match_dbg &&
                     (n1 % 4 == 0) && (n2 % 4 == 0) &&
                     ((reinterpret_cast<uintptr_t>(desc1) | reinterpret_cast<uintptr_t>(desc2)) & 15) == 0;
-    if (tma_path) tma_path = match_make_tmap(&tm1, desc1, P, C, n1) && match_make_tmap(&tm2, desc2, P, C, n2);
+    int tma4 = 0;
+    if (tma_path) {
+        tma4 = env0.match_tma != 3 && match_make_tmap4(&tm1, desc1, P, C, n1) && match_make_tmap4(&tm2, desc2, P, C, n2) ? 1 : 0;
+        if (!tma4) tma_path = match_make_tmap(&tm1, desc1, P, C, n1) && match_make_tmap(&tm2, desc2, P, C, n2);
+    }
     if (tma_path) {
         const int norm_x = (L.n1p > L.n2p ? L.n1p : L.n2p) / 32;
         match_norm_kernel<<<dim3(norm_x, P, 2), 256, 0, st>>>(side1, side2, C);
@@ -1075,7 +1104,7 @@ extern "C" int ri_mutual_nn_tf32x3(const float* desc1, const float* desc2, int P
         if (ptotal < clusters) clusters = (int)ptotal;
         match_gemm_pair_kernel<true><<<2 * clusters, kPThreadsP, smem2, st>>>(nullptr, nullptr, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp,
                                                                               ptiles_m, tiles_n, (int)ptotal, rowkey, colkey, nullptr,
-                                                                              tm1, tm2);
+                                                                              tm1, tm2, tma4);
         RI_LAUNCH_CHECK();
         int* mutual_t = reinterpret_cast<int*>(ws + L.mutual);
         match_unpack_kernel<<<dim3((n1 + 255) / 256, P), 256, 0, st>>>(n1, n2, L.n1p, L.n2p, rowkey, colkey, corr12, mutual_t);
@@ -1109,7 +1138,7 @@ extern "C" int ri_mutual_nn_tf32x3(const float* desc1, const float* desc2, int P
             if (ptotal < clusters) clusters = (int)ptotal;
             match_gemm_pair_kernel<false><<<2 * clusters, kPThreadsP, smem2, st>>>(img1, img2, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp,
                                                                                  ptiles_m, tiles_n, (int)ptotal, rowkey, colkey, dbg,
-                                                                                 none, none);
+                                                                                 none, none, 0);
         } else {
             RI_KERNEL_SETUP(match_gemm_kernel, true, -1);
             match_gemm_kernel<<<grid, kPThreads, smem, st>>>(img1, img2, nrm1, nrm2, n1, n2, L.n1p, L.n2p, L.Cp, tiles_m, tiles_n,

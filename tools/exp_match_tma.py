@@ -31,15 +31,13 @@ assert L.ri_debug_set_knob(b"RI_MATCH_TMA", 0) == 0
 mm(d1, d2); torch.cuda.synchronize()
 ref = {k: getattr(mm, k).clone() for k in ("corr12", "corr21", "idx1", "idx2", "count")}
 us_prep = t(lambda: mm(d1, d2))
-assert L.ri_debug_set_knob(b"RI_MATCH_TMA", -1) == 0
-for k in ("corr12", "corr21", "idx1", "idx2", "count"):
-    getattr(mm, k).fill_(-5)
-mm(d1, d2); torch.cuda.synchronize()
-got = {k: getattr(mm, k).clone() for k in ref}
-us_tma = t(lambda: mm(d1, d2))
-out = {"shape": [P, C, n1, n2], "us_prepass_path": us_prep, "us_tensor_map_path": us_tma}
-for k in ref:
-    out["equal_" + k] = bool(torch.equal(ref[k], got[k]))
-    if not out["equal_" + k]:
-        out["mismatch_frac_" + k] = float((ref[k] != got[k]).float().mean())
+out = {"shape": [P, C, n1, n2], "us_prepass_path": us_prep}
+for mode, label in ((3, "3d_boxes"), (-1, "default")):
+    assert L.ri_debug_set_knob(b"RI_MATCH_TMA", mode) == 0
+    for k in ("corr12", "corr21", "idx1", "idx2", "count"):
+        getattr(mm, k).fill_(-5)
+    mm(d1, d2); torch.cuda.synchronize()
+    got = {k: getattr(mm, k).clone() for k in ref}
+    out["us_tensor_map_" + label] = t(lambda: mm(d1, d2))
+    out["equal_" + label] = all(bool(torch.equal(ref[k], got[k])) for k in ref)
 print(json.dumps(out))
