@@ -1,5 +1,6 @@
 #!/bin/bash
-OUT=gpurun_out/r2to; mkdir -p $OUT
-for S in "32 512 1024 1024" "3 100 320 704" "2 33 1000 132" "5 128 1024 512 reg" "8 256 512 512"; do
-  timeout 90 python tools/exp_match_tma.py $S 2>&1 | tail -1 | tee -a $OUT/match_tma.txt
-done
+OUT=gpurun_out/r2tp; mkdir -p $OUT
+export RI_REQUIRE_REF=1
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
