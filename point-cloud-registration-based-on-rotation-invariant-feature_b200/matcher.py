@@ -12,12 +12,17 @@ import torch
 __all__ = ['mutual_nn', 'find_correspondence_one_pair', 'MutualMatcher']
 
 
-def mutual_nn(desc1, desc2, point_major=False):
+def mutual_nn(desc1, desc2, point_major=False, want_dist=True):
     """desc1 [P,C,n1], desc2 [P,C,n2] CUDA fp32 (or [P,n,C] with point_major=True).
-    Returns a dict: corr12 [P,n1], corr21 [P,n2] (int32 argmins), dist12 [P,n1] (fp32 distance of each row's nearest),
-    idx1/idx2 [P,n1] (mutual matches in ascending idx1, -1 padded) and count [P]."""
-    c12, c21, d12, i1, i2, cnt = torch.ops.ri.mutual_nn(desc1.float().contiguous(), desc2.float().contiguous(),
-                                                        bool(point_major))
+    Returns a dict: corr12 [P,n1], corr21 [P,n2] (int32 argmins), dist12 [P,n1] (fp32 distance of each row's nearest; absent with
+    want_dist=False — the reference method returns the matches only, and without the distances the library skips a pass over the
+    descriptors and, for channel-major input, the re-tiled image), idx1/idx2 [P,n1] (mutual matches in ascending idx1, -1 padded)
+    and count [P]."""
+    d1, d2 = desc1.float().contiguous(), desc2.float().contiguous()
+    if not want_dist:
+        c12, c21, i1, i2, cnt = torch.ops.ri.mutual_nn_indices(d1, d2, bool(point_major))
+        return {'corr12': c12, 'corr21': c21, 'idx1': i1, 'idx2': i2, 'count': cnt}
+    c12, c21, d12, i1, i2, cnt = torch.ops.ri.mutual_nn(d1, d2, bool(point_major))
     return {'corr12': c12, 'corr21': c21, 'dist12': d12, 'idx1': i1, 'idx2': i2, 'count': cnt}
 
 
@@ -26,7 +31,7 @@ def find_correspondence_one_pair(feat1, feat2, device='cuda'):
     (idx1, idx2) int64 numpy arrays of the mutual matches, exactly the reference's return value."""
     f1 = torch.as_tensor(feat1, dtype=torch.float32).to(device)[None].contiguous()
     f2 = torch.as_tensor(feat2, dtype=torch.float32).to(device)[None].contiguous()
-    r = mutual_nn(f1, f2, point_major=True)
+    r = mutual_nn(f1, f2, point_major=True, want_dist=False)
     n = int(r['count'][0].item())
     return (r['idx1'][0, :n].cpu().numpy().astype(np.int64), r['idx2'][0, :n].cpu().numpy().astype(np.int64))
 

@@ -570,6 +570,45 @@ def _(desc1, desc2, point_major):
     return i(P, n1), i(P, n2), desc1.new_empty((P, n1)), i(P, n1), i(P, n1), i(P)
 
 
+@torch.library.custom_op("ri::mutual_nn_indices", mutates_args=())
+def mutual_nn_indices(desc1: torch.Tensor, desc2: torch.Tensor, point_major: bool) -> tuple[
+        torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The same matcher without the distance output — what the reference method returns: corr12 [P,n1], corr21 [P,n2], idx1, idx2
+    [P,n1] (mutual matches, -1 padded), count [P].  dist12 = NULL lets the library skip the re-evaluation pass and, for
+    channel-major descriptors, the re-tiled image altogether (csrc/matcher.cu, tensor-map path)."""
+    _req(desc1, "desc1", torch.float32); _req(desc2, "desc2", torch.float32)
+    dev = _same_device(desc1, desc2)
+    if desc1.dim() != 3 or desc2.dim() != 3 or desc1.shape[0] != desc2.shape[0]:
+        raise RuntimeError("desc1/desc2 must be [P,C,n] (or [P,n,C]) with the same number of pairs")
+    P = desc1.shape[0]
+    if point_major:
+        n1, C = desc1.shape[1], desc1.shape[2]; n2, C2 = desc2.shape[1], desc2.shape[2]
+    else:
+        C, n1 = desc1.shape[1], desc1.shape[2]; C2, n2 = desc2.shape[1], desc2.shape[2]
+    if C != C2:
+        raise RuntimeError("desc1 and desc2 must have the same number of channels")
+    i32 = torch.int32
+    corr12 = torch.empty((P, n1), dtype=i32, device=dev); corr21 = torch.empty((P, n2), dtype=i32, device=dev)
+    idx1 = torch.empty((P, n1), dtype=i32, device=dev); idx2 = torch.empty((P, n1), dtype=i32, device=dev)
+    count = torch.empty((P,), dtype=i32, device=dev)
+    with torch.cuda.device(dev):
+        nws = _L.ri_mutual_nn_workspace_bytes(P, C, n1, n2)
+        ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+        _check(_L.ri_mutual_nn_tf32x3(desc1.data_ptr(), desc2.data_ptr(), P, C, n1, n2, 1 if point_major else 0,
+                                      corr12.data_ptr(), corr21.data_ptr(), None, idx1.data_ptr(),
+                                      idx2.data_ptr(), count.data_ptr(), ws.data_ptr(), nws, _stream()), "ri_mutual_nn")
+    return corr12, corr21, idx1, idx2, count
+
+
+@mutual_nn_indices.register_fake
+def _(desc1, desc2, point_major):
+    P = desc1.shape[0]
+    n1 = desc1.shape[1] if point_major else desc1.shape[2]
+    n2 = desc2.shape[1] if point_major else desc2.shape[2]
+    i = lambda *s: desc1.new_empty(s, dtype=torch.int32)
+    return i(P, n1), i(P, n2), i(P, n1), i(P, n1), i(P)
+
+
 # ---------------------------------------------------------------------------------------------- grid subsampling (f2)
 @torch.library.custom_op("ri::grid_subsample", mutates_args=())
 def grid_subsample(points: torch.Tensor, features: torch.Tensor, labels: torch.Tensor, grid_size: float) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:

@@ -38,7 +38,7 @@ def registration_metrics(gt_trans, est_trans, pts):
 
 def register_pairs(feat1, feat2, pt1, pt2, func='ransac', **kw):
     """feat1/feat2 [P,C,n] (the extractor's layout), pt1/pt2 [P,n,3], all CUDA -> (T [P,4,4], inliers [P], matches dict)."""
-    m = matcher.mutual_nn(feat1, feat2, point_major=False)
+    m = matcher.mutual_nn(feat1, feat2, point_major=False, want_dist=False)      # the meter uses the matches only
     T, inl = estimate_poses(pt1, pt2, m['idx1'], m['idx2'], m['count'], func=func, **kw)
     return T, inl, m
 
